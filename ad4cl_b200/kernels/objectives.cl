@@ -1,0 +1,259 @@
+/*
+ * objectives.cl -- user objective kernels written in the ad.cl dialect.
+ *
+ * These are the likelihood terms of BASELINE.json configs 1, 3, 4, 5 expressed
+ * exactly the way test/admb/simple.cl:106-141 expresses its own: a __kernel
+ * that receives (gs, gradient_stack, parameters, data, out, size), calls the
+ * ad_* / pad_* operators of the device AD runtime, and stores one ad_variable
+ * per work-item into out[].  The same text is compiled
+ *   - by nvcc / NVRTC against ad4cl_b200/csrc/ad.cuh  (the product), and
+ *   - by gcc against the reference's own ad.cl, or against oracle/ad_port.h
+ *     (the CPU oracle; tests and the CPU baseline only).
+ * Nothing here is specific to either side: plain C99 that is also valid C++.
+ *
+ * Common signature ("objective ABI") for every kernel except linreg2:
+ *   theta : P independent ad_variables, ids 0..P-1
+ *   d0,d1 : two fp64 data arrays
+ *   out   : one ad_variable per work-item (the term that is summed)
+ *   size  : number of work-items that carry data (global size may be larger)
+ *   i0,i1 : two integer shape arguments
+ */
+
+/* ------------------------------------------------------------------------
+ * config 1: sum of squares term of the shipped example (kernel.cl:17-25,
+ * test/admb/simple.cl:123-137): out = ((a*x + b) - y)^2, 4 AD ops.
+ * linreg2_g uses the global-stack family, linreg2_p the block-reserved one.
+ * --------------------------------------------------------------------- */
+__kernel void linreg2_g(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* a,
+        __global struct ad_variable* b,
+        __global double* x,
+        __global double* y,
+        __global struct ad_variable* out, int size) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_variable pred = ad_plus(gs, ad_times_vd(gs, *a, x[id]), *b);
+        struct ad_variable res = ad_minus_vd(gs, pred, y[id]);
+        out[id] = ad_times(gs, res, res);
+    }
+}
+
+__kernel void linreg2_p(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __constant struct ad_variable* a,
+        __constant struct ad_variable* b,
+        __global double* x,
+        __global double* y,
+        __global struct ad_variable* out, int size) {
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_gradient_structure pgs;
+        ad_init(gs, gradient_stack);
+        pad_init(4, &pgs, gs, gradient_stack);
+        struct ad_variable pred = pad_plus(&pgs, pad_times_vd(&pgs, *a, x[id]), *b);
+        struct ad_variable res = pad_minus_vd(&pgs, pred, y[id]);
+        out[id] = pad_times(&pgs, res, res);
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * config 3: regression with P = i0 parameters, X stored [P][size]
+ * (observation-contiguous), y = d1.
+ *   linear  : out = (sum_j theta_j X_ji - y_i)^2            21 ops at P=10
+ *   logistic: out = log(1 + exp(eta)) - y_i * eta           24 ops at P=10
+ * --------------------------------------------------------------------- */
+__kernel void regression_linear(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_variable eta = ad_times_vd(gs, theta[0], d0[id]);
+        for (int j = 1; j < i0; j++) {
+            eta = ad_plus(gs, eta, ad_times_vd(gs, theta[j], d0[(size_t) j * size + id]));
+        }
+        struct ad_variable res = ad_minus_vd(gs, eta, d1[id]);
+        out[id] = ad_times(gs, res, res);
+    }
+}
+
+__kernel void regression_logistic(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_variable eta = ad_times_vd(gs, theta[0], d0[id]);
+        for (int j = 1; j < i0; j++) {
+            eta = ad_plus(gs, eta, ad_times_vd(gs, theta[j], d0[(size_t) j * size + id]));
+        }
+        struct ad_variable softplus = ad_log(gs, ad_plus_vd(gs, ad_exp(gs, eta), 1.0));
+        out[id] = ad_minus(gs, softplus, ad_times_vd(gs, eta, d1[id]));
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * config 4: catch-at-age negative log-likelihood term, P = 100.
+ *   work-item i = rep + R*(year + CAA_YEARS*age), R = i0 replicates, so the
+ *   replicate index is fastest and (year, age) -- hence the whole op sequence
+ *   and every parameter id except the fleet deviation -- is uniform across
+ *   neighbouring work-items.
+ *   theta: [0,49) log recruitment of cohort c = year - age + 9
+ *          [49,89) log F_year   89: a50   90: slope   91: log M
+ *          92: log q   93: log sigma   [94,100) fleet deviations of log q
+ *   d0   : observed log catch (this shard's observations)
+ *   i1   : global index of this shard's first observation (0 on one GPU)
+ *   fleet of a replicate = rep*6/R  (6 contiguous blocks of replicates)
+ * Baranov: Z = M + F_y s_a ; N = R_c exp(-sum_{k<a} Z_{y-a+k,k}) ;
+ *          Chat = F s / Z (1 - exp(-Z)) N q ;
+ *          out = (ln C - ln Chat)^2 / (2 sigma^2) + ln sigma
+ * --------------------------------------------------------------------- */
+#define CAA_YEARS 40
+#define CAA_AGES 10
+#define CAA_LOGF 49
+#define CAA_A50 89
+#define CAA_SLOPE 90
+#define CAA_LOGM 91
+#define CAA_LOGQ 92
+#define CAA_LOGSIGMA 93
+#define CAA_FLEETDEV 94
+#define CAA_FLEETS 6
+
+__kernel void catch_at_age(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        const int R = i0;
+        const int rep = (id + i1) % R;
+        const int cell = (id + i1) / R;
+        const int year = cell % CAA_YEARS;
+        const int age = cell / CAA_YEARS;
+        const int cohort = year - age + (CAA_AGES - 1);
+        const int fleet = (int) (((long long) rep * CAA_FLEETS) / R);
+
+        struct ad_variable M = ad_exp(gs, theta[CAA_LOGM]);
+        struct ad_variable Z = M;
+        struct ad_variable Fs = M;
+        struct ad_variable cumZ = M;
+        int have_cum = 0;
+        /* walk the cohort from age 0 up to this age; the last pass (k == age)
+           leaves this cell's own Z and F*s */
+        for (int k = 0; k <= age; k++) {
+            const int yy = year - age + k;
+            if (yy >= 0) {
+                struct ad_variable arg = ad_times(gs, theta[CAA_SLOPE],
+                        ad_minus_dv(gs, (double) k, theta[CAA_A50]));
+                struct ad_variable sel = ad_divide_dv(gs, 1.0,
+                        ad_plus_vd(gs, ad_exp(gs, ad_times_vd(gs, arg, -1.0)), 1.0));
+                Fs = ad_times(gs, ad_exp(gs, theta[CAA_LOGF + yy]), sel);
+                Z = ad_plus(gs, M, Fs);
+            } else {
+                Z = M; /* no fishery before the first year */
+            }
+            if (k < age) {
+                if (have_cum) {
+                    cumZ = ad_plus(gs, cumZ, Z);
+                } else {
+                    cumZ = Z;
+                    have_cum = 1;
+                }
+            }
+        }
+        struct ad_variable logN = theta[cohort];
+        if (have_cum) {
+            logN = ad_minus(gs, logN, cumZ);
+        }
+        struct ad_variable N = ad_exp(gs, logN);
+        struct ad_variable surv = ad_minus_dv(gs, 1.0, ad_exp(gs, ad_times_vd(gs, Z, -1.0)));
+        struct ad_variable q = ad_exp(gs, ad_plus(gs, theta[CAA_LOGQ], theta[CAA_FLEETDEV + fleet]));
+        struct ad_variable chat = ad_times(gs,
+                ad_times(gs, ad_times(gs, ad_divide(gs, Fs, Z), surv), N), q);
+        struct ad_variable res = ad_minus_dv(gs, d0[id], ad_log(gs, chat));
+        struct ad_variable sigma = ad_exp(gs, theta[CAA_LOGSIGMA]);
+        struct ad_variable two_s2 = ad_times_vd(gs, ad_times(gs, sigma, sigma), 2.0);
+        out[id] = ad_plus(gs, ad_divide(gs, ad_times(gs, res, res), two_s2), theta[CAA_LOGSIGMA]);
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * config 5: tape-length stress.  steps = i0, P = i1, x = d0.
+ *   v_0 = theta_0 * x ;  v_{j+1} = 0.5 v_j + theta_{j mod P} x   (3 ops/step)
+ *   out = v_steps                       L = 3*steps + 1 ops, 4*steps + 1 slots
+ * --------------------------------------------------------------------- */
+__kernel void tape_stress(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        const double x = d0[id];
+        struct ad_variable v = ad_times_vd(gs, theta[0], x);
+        int p = 0;
+        for (int j = 0; j < i0; j++) {
+            v = ad_plus(gs, ad_times_vd(gs, v, 0.5), ad_times_vd(gs, theta[p], x));
+            p = (p + 1 == i1) ? 0 : p + 1;
+        }
+        out[id] = v;
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * op coverage kernel (parity tests only): one work-item = one chain through
+ * every operator of the global-stack family, on data-dependent operands, so
+ * that a single launch compares every value and every partial against the
+ * reference.  theta has 3 parameters; d0 in (0.1, 0.9).
+ * --------------------------------------------------------------------- */
+__kernel void op_zoo(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        const double x = d0[id];
+        struct ad_variable a = ad_times_vd(gs, theta[0], x);          /* in (0,1) */
+        struct ad_variable b = ad_plus_vd(gs, theta[1], x);           /* > 1 */
+        struct ad_variable c = ad_plus_dv(gs, 0.25, theta[2]);
+        struct ad_variable acc = ad_plus(gs, a, b);
+        acc = ad_minus(gs, acc, c);
+        acc = ad_minus_vd(gs, acc, 0.125);
+        acc = ad_minus_dv(gs, 9.0, acc);
+        acc = ad_times(gs, acc, b);
+        acc = ad_times_dv(gs, 0.75, acc);
+        acc = ad_divide(gs, acc, b);
+        acc = ad_divide_vd(gs, acc, 1.5);
+        acc = ad_plus(gs, acc, ad_divide_dv(gs, 2.0, b));
+        ad_plus_eq(gs, &acc, a);
+        ad_plus_eq_d(gs, &acc, 0.5);
+        acc = ad_plus(gs, acc, ad_sin(gs, a));
+        acc = ad_plus(gs, acc, ad_cos(gs, b));
+        acc = ad_plus(gs, acc, ad_tan(gs, a));
+        acc = ad_plus(gs, acc, ad_asin(gs, a));
+        acc = ad_plus(gs, acc, ad_acos(gs, a));
+        acc = ad_plus(gs, acc, ad_atan(gs, b));
+        acc = ad_plus(gs, acc, ad_sinh(gs, a));
+        acc = ad_plus(gs, acc, ad_cosh(gs, a));
+        acc = ad_plus(gs, acc, ad_tanh(gs, b));
+        acc = ad_plus(gs, acc, ad_exp(gs, a));
+        acc = ad_plus(gs, acc, ad_log(gs, b));
+        acc = ad_plus(gs, acc, ad_log10(gs, b));
+        acc = ad_plus(gs, acc, ad_sqrt(gs, b));
+        acc = ad_plus(gs, acc, ad_pow(gs, b, a));
+        acc = ad_plus(gs, acc, ad_pow_vd(gs, b, 1.75));
+        acc = ad_plus(gs, acc, ad_pow_dv(gs, 1.5, a));
+        out[id] = acc;
+    }
+}
