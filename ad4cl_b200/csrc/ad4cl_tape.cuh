@@ -1,0 +1,264 @@
+/*
+ * ad4cl_tape.cuh -- the per-thread Jacobian tape of the B200 AD runtime.
+ *
+ * What the reference does (ad.cl:174-198 and every other operator): reserve a
+ * slot on ONE global stack with atomic_inc, write a 40-byte ad_entry
+ * {dx,id}[2],id,size (ad.cl:75-79) at a 40-byte stride per work-item, and
+ * leave the adjoint sweep to a serial host loop (ad4cl.h:775-802).
+ *
+ * What this file does instead (sm_100a):
+ *   - every thread owns a private tape; a warp's 32 tapes are interleaved into
+ *     ONE contiguous LIFO stream of 384-byte rows
+ *         row s = [ dx of slot s, lanes 0..31 : 256 B ][ id word, lanes 0..31 : 128 B ]
+ *     so a warp-wide push is two fully coalesced stores (2 + 1 cache lines) and
+ *     the forward pass writes / the reverse pass reads strictly sequential
+ *     memory per warp.  The stream lives in an HBM arena sized by RESIDENT
+ *     warps (not by work-items) or in shared memory.
+ *   - a slot is one (partial, operand id) pair: 12 bytes.  An operator with k
+ *     variable operands pushes k slots; the result id is implicit (= position
+ *     of the operator on this thread's tape + number of independents), the
+ *     last slot of an operator carries END in the top bit of its id word.
+ *     That is the 12k-bytes-per-op record of SURVEY.md 8(d).
+ *   - the reverse sweep runs in the same kernel, right after the work-item's
+ *     forward pass.  Adjoints of temporaries live in a shared-memory ring of W
+ *     entries per thread (operands are almost always recent); an operand that
+ *     is W or more operators old is detected at record time and routed to a
+ *     "far" adjoint plane in the arena, flagged in a per-thread bitmap.
+ *   - adjoints of the independents (ids below first_temp) never touch the
+ *     tape: they go to the accumulator the launch selected (ad4cl_entry.cuh).
+ */
+#pragma once
+
+#ifndef __CUDACC_RTC__
+#include <cuda_runtime.h>
+#endif
+
+namespace ad4cl {
+
+constexpr int kEndFlag = (int) 0x80000000u; /* last slot of an operator */
+constexpr int kNopFlag = 0x40000000;        /* slot carries no partial (leaf variable) */
+constexpr int kIdMask = 0x3FFFFFFF;
+constexpr int kNoId = -1;                   /* "no output written" */
+
+constexpr int kRowBytes = 384;              /* 32 lanes x (8 B partial + 4 B id word) */
+constexpr int kRowIdOffset = 256;
+constexpr int kFarRowBytes = 256;           /* far adjoints: 32 lanes x 8 B per operator */
+constexpr int kBitsRowBytes = 128;          /* far bitmap: 32 lanes x 4 B per 32 operators */
+
+enum Status : int {
+    kOk = 0,
+    kErrTapeOverflow = 1,   /* more slots / operators than the arena column holds */
+    kErrWindow = 2,         /* far operand met while the far plane is disabled */
+};
+
+struct ThreadTape {
+    char* cur;            /* address of this lane's partial in the next free row */
+    int id_off;           /* byte offset from a row's partial to its id word, this lane */
+    unsigned nslots;      /* slots pushed by the current work-item */
+    unsigned kept;        /* of which actually stored (== nslots unless the tape overflowed) */
+    unsigned cap_slots;
+    int nops;             /* operators recorded by the current work-item */
+    int cap_ops;
+    int first_temp;       /* number of independents: ids >= first_temp are tape positions */
+    int window;           /* W, a power of two */
+    char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
+    char* far_bits;       /* this lane's far bitmap column (row stride kBitsRowBytes) */
+    int status;           /* sticky Status bits */
+    long long total_ops;  /* statistics over all work-items of this thread */
+    long long total_slots;
+};
+
+/* Bytes one warp needs in the arena for cap_slots slots and cap_ops operators. */
+__host__ __device__ inline size_t warp_region_bytes(unsigned cap_slots, int cap_ops, bool far) {
+    size_t b = (size_t) cap_slots * kRowBytes;
+    if (far) {
+        b += (size_t) cap_ops * kFarRowBytes;
+        b += (size_t) ((cap_ops + 31) / 32) * kBitsRowBytes;
+    }
+    return (b + 127) & ~(size_t) 127;
+}
+
+__device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsigned cap_slots,
+        int cap_ops, int first_temp, int window, bool far) {
+    const int lane = threadIdx.x & 31;
+    t.cur = warp_region + lane * 8;
+    t.id_off = kRowIdOffset - lane * 4;
+    t.nslots = 0;
+    t.kept = 0;
+    t.cap_slots = cap_slots;
+    t.nops = 0;
+    t.cap_ops = cap_ops;
+    t.first_temp = first_temp;
+    t.window = window;
+    if (far) {
+        char* fa = warp_region + (size_t) cap_slots * kRowBytes;
+        t.far_adj = fa + lane * 8;
+        t.far_bits = fa + (size_t) cap_ops * kFarRowBytes + lane * 4;
+    } else {
+        t.far_adj = nullptr;
+        t.far_bits = nullptr;
+    }
+    t.status = kOk;
+    t.total_ops = 0;
+    t.total_slots = 0;
+}
+
+/* An operand that is `window` or more operators old cannot use the ring. */
+__device__ __forceinline__ void tape_note_far(ThreadTape* t, int pos) {
+    if (t->far_adj == nullptr) {
+        t->status |= kErrWindow;
+        return;
+    }
+    unsigned* word = reinterpret_cast<unsigned*> (t->far_bits + (size_t) (pos >> 5) * kBitsRowBytes);
+    const unsigned bit = 1u << (pos & 31);
+    const unsigned old = *word;
+    if (!(old & bit)) {
+        *word = old | bit;
+        *reinterpret_cast<double*> (t->far_adj + (size_t) pos * kFarRowBytes) = 0.0;
+    }
+}
+
+/* Push one (partial, operand) slot.  `flags` is 0, kEndFlag or kEndFlag|kNopFlag. */
+__device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
+    if (t->nslots < t->cap_slots && t->nops < t->cap_ops) {
+        if (id >= t->first_temp && !(flags & kNopFlag)) {
+            const int pos = id - t->first_temp;
+            if (t->nops - pos >= t->window) tape_note_far(t, pos);
+        }
+        *reinterpret_cast<double*> (t->cur) = dx;
+        *reinterpret_cast<int*> (t->cur + t->id_off) = id | flags;
+        t->cur += kRowBytes;
+        t->kept++;
+    } else {
+        t->status |= kErrTapeOverflow;
+    }
+    t->nslots++;
+}
+
+/* Close the operator whose slots were just pushed; returns its result id. */
+__device__ __forceinline__ int tape_close_op(ThreadTape* t) {
+    return t->first_temp + t->nops++;
+}
+
+/* Forget the current work-item's tape (the arena column is reused). */
+__device__ __forceinline__ void tape_rewind(ThreadTape& t) {
+    t.total_ops += t.nops;
+    t.total_slots += t.nslots;
+    t.cur -= (size_t) t.kept * kRowBytes;
+    t.nslots = 0;
+    t.kept = 0;
+    t.nops = 0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, off);
+    }
+    return v;
+}
+
+/* Where adjoints of the independents go during the sweep. */
+enum AccMode : int {
+    kAccThread = 0, /* per-thread accumulators in shared memory, tree-reduced at the end */
+    kAccWarp = 1,   /* warp-shuffle reduce per contribution, per-warp accumulators */
+    kAccGlobal = 2, /* fp64 RED into a global gradient array (many independents) */
+};
+
+struct SweepTarget {
+    double* ring;        /* this thread's ring column: entry r at ring[r * stride] */
+    int stride;          /* block size */
+    int mode;
+    double* thread_acc;  /* kAccThread: this thread's column, parameter p at thread_acc[p * stride] */
+    double* warp_acc;    /* kAccWarp: this warp's row of P accumulators */
+    double* global_acc;  /* kAccGlobal: gradient array indexed by id */
+};
+
+__device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param, int id, double c) {
+    if (T.mode == kAccThread) {
+        if (is_param) T.thread_acc[(size_t) id * T.stride] += c;
+    } else if (T.mode == kAccWarp) {
+        /* all 32 lanes arrive here together; group lanes by parameter id in
+           lowest-lane-first order so the summation order is fixed */
+        unsigned pending = __ballot_sync(0xffffffffu, is_param);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const int lid = __shfl_sync(0xffffffffu, id, leader);
+            const bool mine = is_param && id == lid;
+            const unsigned members = __ballot_sync(0xffffffffu, mine);
+            const double v = warp_sum(mine ? c : 0.0);
+            if ((threadIdx.x & 31) == 0) T.warp_acc[lid] += v;
+            pending &= ~members;
+        }
+    } else {
+        if (is_param) atomicAdd(&T.global_acc[id], c);
+    }
+}
+
+/*
+ * Reverse sweep of the current work-item's tape, seeded with 1 at `out_id`.
+ * Restates the loop of ad4cl.h:786-797 (w = g[id]; g[id] = 0; g[operand] +=
+ * w * dx) on the slot stream: the adjoint of the operator at position p is
+ * popped from the ring when its END slot is met, and each slot scatters w * dx
+ * to the ring (recent temporaries), the far plane (old temporaries) or the
+ * accumulator (independents).  All lanes of the warp iterate together (tapes
+ * of neighbouring work-items normally have identical shape).
+ */
+__device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T) {
+    const int first_temp = t.first_temp;
+    const int wmask = t.window - 1;
+    int p = t.nops;
+    unsigned s = t.kept;
+    char* cur = t.cur;
+    const int seed_pos = out_id - first_temp;
+    sweep_param(T, out_id >= 0 && out_id < first_temp, out_id, 1.0);
+
+    double w = 0.0;
+    unsigned bits = 0;
+    int bits_word = -1;
+    while (__any_sync(0xffffffffu, s > 0)) {
+        const bool act = s > 0;
+        double dx = 0.0;
+        int idw = kNopFlag;
+        if (act) {
+            cur -= kRowBytes;
+            dx = *reinterpret_cast<const double*> (cur);
+            idw = *reinterpret_cast<const int*> (cur + t.id_off);
+            --s;
+        }
+        if (idw & kEndFlag) {
+            --p;
+            double* r = T.ring + (size_t) (p & wmask) * T.stride;
+            w = *r;
+            *r = 0.0;
+            if (p == seed_pos) w += 1.0;
+            if (t.far_adj != nullptr) {
+                const int word = p >> 5;
+                if (word != bits_word) {
+                    if (bits_word >= 0 && bits != 0)
+                        *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
+                    bits_word = word;
+                    bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) word * kBitsRowBytes);
+                }
+                if ((bits >> (p & 31)) & 1u)
+                    w += *reinterpret_cast<const double*> (t.far_adj + (size_t) p * kFarRowBytes);
+            }
+        }
+        const int id = idw & kIdMask;
+        const double c = w * dx;
+        const bool live = act && !(idw & kNopFlag);
+        if (live && id >= first_temp) {
+            const int pos = id - first_temp;
+            if (p - pos < t.window) {
+                T.ring[(size_t) (pos & wmask) * T.stride] += c;
+            } else if (t.far_adj != nullptr) {
+                *reinterpret_cast<double*> (t.far_adj + (size_t) pos * kFarRowBytes) += c;
+            }
+        }
+        sweep_param(T, live && id < first_temp, id, c);
+    }
+    if (bits_word >= 0 && bits != 0)
+        *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
+}
+
+} // namespace ad4cl

@@ -1,0 +1,785 @@
+/*
+ * shim.cu -- implementation of the C ABI declared in include/ad4cl_cuda.h.
+ *
+ * Host-side orchestration only: resource sizing, argument marshalling, the
+ * three launches of one evaluation (pack parameters, fused record+sweep+block
+ * reduction, fixed-order second stage) and the two small PCIe copies.  The
+ * arithmetic lives in ad.cuh / ad4cl_tape.cuh / ad4cl_entry.cuh.
+ *
+ * No CPU path exists here: every entry point needs a CUDA device.
+ */
+#include "../../include/ad4cl_cuda.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ad4cl_builtin.h"
+#include "ad4cl_entry.cuh"
+#include "ad4cl_reduce.cuh"
+
+extern "C" const ad4cl_builtin_row ad4cl_builtin_table_fixed[];
+extern "C" const ad4cl_builtin_row ad4cl_builtin_table_quirks[];
+extern "C" const char* const ad4cl_embedded_header_names[];
+extern "C" const char* const ad4cl_embedded_header_texts[];
+extern "C" const int ad4cl_embedded_header_count;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(AD4CL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                    __FILE__, __LINE__);                                                    \
+    } while (0)
+
+/* writes {theta[i], id = i} for the V arguments (ad_init_var, ad4cl.h:90-93) */
+__global__ void pack_params(const double* __restrict__ theta, struct ad_variable* __restrict__ params, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        params[i].value = theta[i];
+        params[i].id = i;
+    }
+}
+
+/* ---- lazily bound driver API + NVRTC (keeps the library loadable on a box without a GPU) ---- */
+struct DriverApi {
+    CUresult (*cuModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*cuModuleUnload)(CUmodule) = nullptr;
+    CUresult (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+            unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*cuGetErrorString)(CUresult, const char**) = nullptr;
+    bool ok = false;
+};
+
+DriverApi& driver() {
+    static DriverApi d;
+    if (d.ok) return d;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return d;
+#define BIND(name, sym) d.name = reinterpret_cast<decltype(d.name)> (dlsym(h, sym))
+    BIND(cuModuleLoadData, "cuModuleLoadData");
+    BIND(cuModuleUnload, "cuModuleUnload");
+    BIND(cuModuleGetFunction, "cuModuleGetFunction");
+    BIND(cuLaunchKernel, "cuLaunchKernel");
+    BIND(cuFuncSetAttribute, "cuFuncSetAttribute");
+    BIND(cuOccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    BIND(cuGetErrorString, "cuGetErrorString");
+#undef BIND
+    d.ok = d.cuModuleLoadData && d.cuModuleGetFunction && d.cuLaunchKernel && d.cuFuncSetAttribute
+            && d.cuOccupancyMaxActiveBlocksPerMultiprocessor;
+    return d;
+}
+
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct NvrtcApi {
+    int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+NvrtcApi& nvrtc() {
+    static NvrtcApi n;
+    if (n.ok) return n;
+    void* h = nullptr;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+        "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return n;
+#define BIND(name, sym) n.name = reinterpret_cast<decltype(n.name)> (dlsym(h, sym))
+    BIND(CreateProgram, "nvrtcCreateProgram");
+    BIND(DestroyProgram, "nvrtcDestroyProgram");
+    BIND(CompileProgram, "nvrtcCompileProgram");
+    BIND(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    BIND(GetProgramLog, "nvrtcGetProgramLog");
+    BIND(GetCUBINSize, "nvrtcGetCUBINSize");
+    BIND(GetCUBIN, "nvrtcGetCUBIN");
+    BIND(GetErrorString, "nvrtcGetErrorString");
+#undef BIND
+    n.ok = n.CreateProgram && n.CompileProgram && n.GetCUBINSize && n.GetCUBIN && n.GetProgramLogSize
+            && n.GetProgramLog && n.DestroyProgram;
+    return n;
+}
+
+struct Arg {
+    char kind = 0;
+    bool set = false;
+    ad4cl_buffer* buf = nullptr;
+    int ival = 0;
+    double dval = 0.0;
+    int first_id = -1, count = 0;   /* V bound to the packed parameter array */
+    void* ptr_storage = nullptr;    /* what the launch's void** points at */
+};
+
+int pow2_at_least(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+} // namespace
+
+struct ad4cl_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+};
+
+struct ad4cl_buffer {
+    ad4cl_context* ctx = nullptr;
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+};
+
+struct ad4cl_kernel {
+    ad4cl_context* ctx = nullptr;
+    std::string name, signature;
+    const void* entry = nullptr;   /* ahead-of-time kernel (runtime API handle) */
+    CUmodule module = nullptr;     /* NVRTC kernel */
+    CUfunction function = nullptr;
+    std::vector<Arg> args;
+    ad4cl_kernel_config cfg{};
+    bool configured = false;
+
+    /* resources derived from (cfg, nparams); rebuilt when either changes */
+    bool ready = false;
+    int nparams = -1;
+    int block = 0, grid = 0;
+    size_t smem = 0, arena_bytes = 0;
+    ad4cl::LaunchInfo L{};
+    long long data_items = 0;
+    struct ad_variable* params_dev = nullptr;
+    double* theta_dev = nullptr;
+    double* partials = nullptr;
+    double* result_dev = nullptr;
+    double* global_grad = nullptr;
+    int* status_dev = nullptr;
+    char* arena = nullptr;
+    double* theta_pinned = nullptr;
+    double* result_pinned = nullptr;
+    int* status_pinned = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ad4cl_eval_stats stats{};
+
+    void release() {
+        cudaFree(params_dev); cudaFree(theta_dev); cudaFree(partials); cudaFree(result_dev);
+        cudaFree(global_grad); cudaFree(status_dev); cudaFree(arena);
+        cudaFreeHost(theta_pinned); cudaFreeHost(result_pinned); cudaFreeHost(status_pinned);
+        params_dev = nullptr; theta_dev = nullptr; partials = nullptr; result_dev = nullptr;
+        global_grad = nullptr; status_dev = nullptr; arena = nullptr;
+        theta_pinned = nullptr; result_pinned = nullptr; status_pinned = nullptr;
+        ready = false;
+    }
+};
+
+namespace {
+
+int signature_ok(const char* s) {
+    if (!s || !*s) return 0;
+    int outs = 0;
+    for (const char* p = s; *p; p++) {
+        if (!strchr("GSOVDIid", *p)) return 0;
+        if (*p == 'O') outs++;
+    }
+    return outs == 1;
+}
+
+ad4cl_kernel* new_kernel(ad4cl_context* ctx, const char* name, const char* sig) {
+    ad4cl_kernel* k = new ad4cl_kernel();
+    k->ctx = ctx;
+    k->name = name;
+    k->signature = sig;
+    k->args.resize(strlen(sig));
+    for (size_t i = 0; i < k->args.size(); i++) {
+        k->args[i].kind = sig[i];
+        if (strchr("GSO", sig[i])) k->args[i].set = true;
+    }
+    ad4cl_cuda_kernel_config_default(&k->cfg);
+    return k;
+}
+
+int occupancy(ad4cl_kernel* k, int block, size_t smem, int* blocks) {
+    if (k->entry) {
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(k->entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k->entry, block, smem));
+    } else {
+        DriverApi& d = driver();
+        if (smem > 48 * 1024) {
+            CUresult r = d.cuFuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) smem);
+            if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed: %d", smem, (int) r);
+        }
+        CUresult r = d.cuOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k->function, block, smem);
+        if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuOccupancyMaxActiveBlocksPerMultiprocessor failed: %d", (int) r);
+    }
+    return AD4CL_OK;
+}
+
+/* size every device resource for `nparams` independents */
+int prepare(ad4cl_kernel* k, int nparams) {
+    if (k->ready && k->nparams == nparams) return AD4CL_OK;
+    if (!k->configured) return fail(AD4CL_ERR_INVALID, "kernel %s: call ad4cl_cuda_kernel_configure first", k->name.c_str());
+    if (nparams < 0) return fail(AD4CL_ERR_INVALID, "nparams < 0");
+    k->release();
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    const ad4cl_kernel_config& c = k->cfg;
+
+    long long g0 = c.global_size[0], g1 = c.global_size[1] > 0 ? c.global_size[1] : 1;
+    int l0 = c.local_size[0], l1 = c.local_size[1] > 0 ? c.local_size[1] : 1;
+    if (g0 <= 0) return fail(AD4CL_ERR_INVALID, "global_size[0] must be positive");
+    if (l0 <= 0) {
+        l0 = g1 > 1 ? 16 : 256;
+        l1 = g1 > 1 ? 16 : 1;
+    }
+    const int block = l0 * l1;
+    if (block > AD4CL_MAX_BLOCK || block % 32 != 0)
+        return fail(AD4CL_ERR_INVALID, "work-group size %d must be a multiple of 32 and <= %d", block, AD4CL_MAX_BLOCK);
+    /* pad the NDRange to whole work-groups; kernels guard with `id < size` (simple.cl:121) */
+    g0 = (g0 + l0 - 1) / l0 * l0;
+    g1 = (g1 + l1 - 1) / l1 * l1;
+    if (g0 >= (1LL << 31) || g0 * g1 >= (1LL << 40)) return fail(AD4CL_ERR_INVALID, "NDRange too large");
+    k->data_items = c.global_size[0] * (c.global_size[1] > 0 ? c.global_size[1] : 1);
+
+    int acc = c.acc_mode;
+    if (acc == AD4CL_ACC_AUTO) acc = nparams <= 16 ? AD4CL_ACC_THREAD : (nparams <= 4096 ? AD4CL_ACC_WARP : AD4CL_ACC_GLOBAL);
+    const int max_ops = std::max(c.max_ops, 1);
+    const unsigned cap_slots = (unsigned) (c.max_slots > 0 ? c.max_slots : 2 * max_ops);
+    const int cap_ops = max_ops + 1;
+    const bool far = c.far_plane != 0;
+    int window = c.window > 0 ? pow2_at_least(c.window) : (far ? 16 : pow2_at_least(cap_ops));
+    int tier = c.tape_tier;
+    if (tier == AD4CL_TAPE_AUTO) tier = AD4CL_TAPE_HBM;
+
+    const size_t smem = ad4cl::entry_smem_bytes(block, nparams, window, acc, tier == AD4CL_TAPE_SHARED,
+            cap_slots, cap_ops, far);
+    if (smem > k->ctx->prop.sharedMemPerBlockOptin)
+        return fail(AD4CL_ERR_INVALID, "kernel %s needs %zu B of shared memory per block (limit %zu): "
+                "lower window/local size or use AD4CL_ACC_WARP", k->name.c_str(), smem,
+                (size_t) k->ctx->prop.sharedMemPerBlockOptin);
+    int per_sm = 0;
+    int rc = occupancy(k, block, smem, &per_sm);
+    if (rc != AD4CL_OK) return rc;
+    if (per_sm < 1) return fail(AD4CL_ERR_INVALID, "kernel %s does not fit on an SM (block %d, smem %zu)", k->name.c_str(), block, smem);
+    if (c.blocks_per_sm > 0) per_sm = std::min(per_sm, c.blocks_per_sm);
+    const long long ngroups = (g0 / l0) * (g1 / l1);
+    int grid = (int) std::min<long long>((long long) k->ctx->prop.multiProcessorCount * per_sm, ngroups);
+    grid = std::max(grid, 1);
+
+    const size_t region = ad4cl::warp_region_bytes(cap_slots, cap_ops, far);
+    const size_t arena_bytes = tier == AD4CL_TAPE_SHARED ? 0 : (size_t) grid * (block / 32) * region;
+    const int ncols = nparams + 3;
+
+    CUDA_TRY(cudaMalloc(&k->params_dev, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
+    CUDA_TRY(cudaMalloc(&k->theta_dev, sizeof (double) * (size_t) std::max(nparams, 1)));
+    CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) grid * ncols));
+    CUDA_TRY(cudaMalloc(&k->result_dev, sizeof (double) * (size_t) ncols));
+    CUDA_TRY(cudaMalloc(&k->status_dev, sizeof (int)));
+    CUDA_TRY(cudaMemset(k->status_dev, 0, sizeof (int)));
+    if (acc == AD4CL_ACC_GLOBAL) CUDA_TRY(cudaMalloc(&k->global_grad, sizeof (double) * (size_t) std::max(nparams, 1)));
+    if (arena_bytes) {
+        cudaError_t e = cudaMalloc(&k->arena, arena_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(AD4CL_ERR_NOMEM, "tape arena of %zu bytes (%d warps x %zu) does not fit: lower blocks_per_sm or max_ops",
+                    arena_bytes, grid * (block / 32), region);
+        }
+        CUDA_TRY(cudaMemset(k->arena, 0, arena_bytes)); /* far bitmaps must start clear */
+    }
+    CUDA_TRY(cudaMallocHost(&k->theta_pinned, sizeof (double) * (size_t) std::max(nparams, 1)));
+    CUDA_TRY(cudaMallocHost(&k->result_pinned, sizeof (double) * (size_t) ncols));
+    CUDA_TRY(cudaMallocHost(&k->status_pinned, sizeof (int)));
+    if (!k->ev0) CUDA_TRY(cudaEventCreate(&k->ev0));
+    if (!k->ev1) CUDA_TRY(cudaEventCreate(&k->ev1));
+
+    ad4cl::LaunchInfo& L = k->L;
+    L.n_items = g0 * g1;
+    L.g0 = (int) g0;
+    L.l0 = l0;
+    L.nparams = nparams;
+    L.recording = 1;
+    L.acc_mode = acc;
+    L.window = window;
+    L.use_far = far ? 1 : 0;
+    L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
+    L.cap_slots = cap_slots;
+    L.cap_ops = cap_ops;
+    L.arena = k->arena;
+    L.warp_region = region;
+    L.partials = k->partials;
+    L.global_grad = k->global_grad;
+    L.status = k->status_dev;
+
+    k->block = block;
+    k->grid = grid;
+    k->smem = smem;
+    k->arena_bytes = arena_bytes;
+    k->nparams = nparams;
+    k->stats.grid = grid;
+    k->stats.block = block;
+    k->stats.smem_bytes = smem;
+    k->stats.arena_bytes = arena_bytes;
+    k->ready = true;
+    return AD4CL_OK;
+}
+
+/* enqueue pack + fused kernel + second stage on the context's stream */
+int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue) {
+    cudaStream_t st = k->ctx->stream;
+    const int P = k->nparams;
+    if (P > 0) {
+        pack_params<<<(P + 127) / 128, 128, 0, st>>>(theta_dev, k->params_dev, P);
+    }
+    ad4cl::LaunchInfo L = k->L;
+    L.recording = want_gradient ? 1 : 0;
+    if (k->global_grad && want_gradient)
+        CUDA_TRY(cudaMemsetAsync(k->global_grad, 0, sizeof (double) * (size_t) std::max(P, 1), st));
+
+    /* marshal: LaunchInfo first, then the user kernel's non-runtime parameters in order */
+    std::vector<void*> argv;
+    argv.push_back(&L);
+    for (size_t i = 0; i < k->args.size(); i++) {
+        Arg& a = k->args[i];
+        if (strchr("GSO", a.kind)) continue;
+        if (!a.set) return fail(AD4CL_ERR_INVALID, "kernel %s: argument %zu ('%c') is not set", k->name.c_str(), i, a.kind);
+        switch (a.kind) {
+            case 'V':
+                if (a.first_id >= 0) {
+                    if (a.first_id + a.count > P)
+                        return fail(AD4CL_ERR_INVALID, "kernel %s: argument %zu binds independents [%d,%d) but nparams = %d",
+                                k->name.c_str(), i, a.first_id, a.first_id + a.count, P);
+                    a.ptr_storage = k->params_dev + a.first_id;
+                } else {
+                    a.ptr_storage = a.buf->ptr;
+                }
+                argv.push_back(&a.ptr_storage);
+                break;
+            case 'D':
+            case 'I':
+                a.ptr_storage = a.buf ? a.buf->ptr : nullptr;
+                argv.push_back(&a.ptr_storage);
+                break;
+            case 'i':
+                argv.push_back(&a.ival);
+                break;
+            case 'd':
+                argv.push_back(&a.dval);
+                break;
+        }
+    }
+    if (k->entry) {
+        CUDA_TRY(cudaLaunchKernel(k->entry, dim3(k->grid), dim3(k->block), argv.data(), k->smem, st));
+    } else {
+        CUresult r = driver().cuLaunchKernel(k->function, k->grid, 1, 1, k->block, 1, 1, (unsigned) k->smem,
+                (CUstream) st, argv.data(), nullptr);
+        if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuLaunchKernel(%s) failed: %d", k->name.c_str(), (int) r);
+    }
+    const int ncols = P + 3;
+    const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
+    ad4cl_reduce_partials<<<ncols, 256, 0, st>>>(k->partials, k->grid, ncols, P,
+            want_gradient ? k->global_grad : nullptr, apply_epilogue ? k->cfg.epilogue : 0, n_obs, result_dev);
+    CUDA_TRY(cudaGetLastError());
+    return AD4CL_OK;
+}
+
+int status_to_error(ad4cl_kernel* k, int st) {
+    if (st == 0) return AD4CL_OK;
+    /* leave the arena clean for the next evaluation (far bitmaps may be dirty) */
+    if (k->arena) cudaMemsetAsync(k->arena, 0, k->arena_bytes, k->ctx->stream);
+    cudaMemsetAsync(k->status_dev, 0, sizeof (int), k->ctx->stream);
+    cudaStreamSynchronize(k->ctx->stream);
+    if (st & ad4cl::kErrTapeOverflow)
+        return fail(AD4CL_ERR_TAPE_OVERFLOW, "kernel %s: a work-item recorded more than max_ops=%d operators / %u slots "
+                "(the reference overflows its stack silently here, SURVEY Q8)", k->name.c_str(), k->cfg.max_ops, k->L.cap_slots);
+    return fail(AD4CL_ERR_WINDOW, "kernel %s: an operand older than window=%d operators was used and far_plane is off",
+            k->name.c_str(), k->L.window);
+}
+
+} // namespace
+
+/* ============================================================ C ABI */
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* ad4cl_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int ad4cl_cuda_init(int device, ad4cl_context** out) {
+    if (!out) return fail(AD4CL_ERR_INVALID, "ctx is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(AD4CL_ERR_CUDA, "no CUDA device (%s): libad4cl_cuda has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(AD4CL_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    ad4cl_context* c = new ad4cl_context();
+    c->device = device;
+    CUDA_TRY(cudaGetDeviceProperties(&c->prop, device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    *out = c;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_shutdown(ad4cl_context* ctx) {
+    if (!ctx) return AD4CL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return AD4CL_OK;
+}
+
+void* ad4cl_cuda_stream(ad4cl_context* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
+
+int ad4cl_cuda_use_stream(ad4cl_context* ctx, void* cuda_stream) {
+    if (!ctx) return fail(AD4CL_ERR_INVALID, "ctx is NULL");
+    ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_device_sm_count(ad4cl_context* ctx) { return ctx ? ctx->prop.multiProcessorCount : 0; }
+
+int ad4cl_cuda_buffer_create(ad4cl_context* ctx, size_t bytes, ad4cl_buffer** out) {
+    if (!ctx || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ad4cl_buffer* b = new ad4cl_buffer();
+    b->ctx = ctx;
+    b->bytes = bytes;
+    cudaError_t e = cudaMalloc(&b->ptr, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) {
+        delete b;
+        cudaGetLastError();
+        return fail(AD4CL_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    *out = b;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_buffer_wrap(ad4cl_context* ctx, void* device_ptr, size_t bytes, ad4cl_buffer** out) {
+    if (!ctx || !out || !device_ptr) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    ad4cl_buffer* b = new ad4cl_buffer();
+    b->ctx = ctx;
+    b->ptr = device_ptr;
+    b->bytes = bytes;
+    b->owned = false;
+    *out = b;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_buffer_upload(ad4cl_buffer* buf, size_t offset, const void* host, size_t bytes) {
+    if (!buf || (!host && bytes)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (offset + bytes > buf->bytes) return fail(AD4CL_ERR_INVALID, "upload of %zu bytes at %zu exceeds buffer of %zu", bytes, offset, buf->bytes);
+    CUDA_TRY(cudaSetDevice(buf->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync((char*) buf->ptr + offset, host, bytes, cudaMemcpyHostToDevice, buf->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(buf->ctx->stream)); /* blocking, like enqueueWriteBuffer(CL_TRUE) */
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_buffer_download(ad4cl_buffer* buf, size_t offset, void* host, size_t bytes) {
+    if (!buf || (!host && bytes)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (offset + bytes > buf->bytes) return fail(AD4CL_ERR_INVALID, "download of %zu bytes at %zu exceeds buffer of %zu", bytes, offset, buf->bytes);
+    CUDA_TRY(cudaSetDevice(buf->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(host, (char*) buf->ptr + offset, bytes, cudaMemcpyDeviceToHost, buf->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(buf->ctx->stream));
+    return AD4CL_OK;
+}
+
+void* ad4cl_cuda_buffer_device_ptr(ad4cl_buffer* buf) { return buf ? buf->ptr : nullptr; }
+
+int ad4cl_cuda_buffer_free(ad4cl_buffer* buf) {
+    if (!buf) return AD4CL_OK;
+    if (buf->owned) {
+        cudaSetDevice(buf->ctx->device);
+        cudaFree(buf->ptr);
+    }
+    delete buf;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_builtin_count(void) {
+    int n = 0;
+    while (ad4cl_builtin_table_fixed[n].name) n++;
+    return n;
+}
+const char* ad4cl_cuda_builtin_name(int i) {
+    return (i >= 0 && i < ad4cl_cuda_builtin_count()) ? ad4cl_builtin_table_fixed[i].name : nullptr;
+}
+const char* ad4cl_cuda_builtin_signature(int i) {
+    return (i >= 0 && i < ad4cl_cuda_builtin_count()) ? ad4cl_builtin_table_fixed[i].signature : nullptr;
+}
+
+int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int reference_quirks, ad4cl_kernel** out) {
+    if (!ctx || !name || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    const ad4cl_builtin_row* tab = reference_quirks ? ad4cl_builtin_table_quirks : ad4cl_builtin_table_fixed;
+    for (const ad4cl_builtin_row* r = tab; r->name; r++) {
+        if (strcmp(r->name, name) == 0) {
+            ad4cl_kernel* k = new_kernel(ctx, name, r->signature);
+            k->entry = r->entry;
+            k->cfg.reference_quirks = reference_quirks;
+            *out = k;
+            return AD4CL_OK;
+        }
+    }
+    return fail(AD4CL_ERR_INVALID, "no built-in kernel named '%s'", name);
+}
+
+int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const char* entry,
+        const char* signature, const char* options, int reference_quirks, ad4cl_kernel** out) {
+    if (!ctx || !source || !entry || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (!signature_ok(signature)) return fail(AD4CL_ERR_INVALID, "bad signature '%s' (letters GSOVDIid, exactly one O)", signature ? signature : "");
+    NvrtcApi& n = nvrtc();
+    if (!n.ok) return fail(AD4CL_ERR_COMPILE, "libnvrtc could not be loaded: %s", dlerror());
+    if (!driver().ok) return fail(AD4CL_ERR_CUDA, "libcuda.so.1 could not be loaded");
+
+    /* translation unit = OpenCL prelude + user text + generated entry */
+    std::string params, call;
+    for (size_t i = 0; signature[i]; i++) {
+        char nm[32];
+        snprintf(nm, sizeof nm, "a%zu", i);
+        const char c = signature[i];
+        const char* passed = c == 'G' ? "gs" : c == 'S' ? "gradient_stack" : c == 'O' ? "out" : nm;
+        if (!call.empty()) call += ", ";
+        call += passed;
+        const char* type = c == 'V' ? "struct ad_variable* " : c == 'D' ? "double* " : c == 'I' ? "int* "
+                : c == 'i' ? "int " : c == 'd' ? "double " : nullptr;
+        if (type) {
+            if (!params.empty()) params += ", ";
+            params += type;
+            params += nm;
+        }
+    }
+    std::string tu = "#include \"ad4cl_opencl_compat.cuh\"\n#line 1 \"user_kernel.cl\"\n";
+    tu += source;
+    tu += "\n#line 1 \"ad4cl_generated_entry\"\nAD4CL_OBJECTIVE_ENTRY(";
+    tu += entry;
+    tu += ", (" + params + "), (" + call + "))\n";
+
+    nvrtcProgram prog = nullptr;
+    int rc = n.CreateProgram(&prog, tu.c_str(), "ad4cl_user.cu", ad4cl_embedded_header_count,
+            ad4cl_embedded_header_texts, ad4cl_embedded_header_names);
+    if (rc != 0) return fail(AD4CL_ERR_COMPILE, "nvrtcCreateProgram failed: %d", rc);
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
+        std::string("-DAD4CL_REFERENCE_QUIRKS=") + (reference_quirks ? "1" : "0")};
+    if (options) {
+        std::string o(options);
+        size_t pos = 0;
+        while (pos < o.size()) {
+            size_t sp = o.find(' ', pos);
+            if (sp == std::string::npos) sp = o.size();
+            if (sp > pos) opts.push_back(o.substr(pos, sp - pos));
+            pos = sp + 1;
+        }
+    }
+    std::vector<const char*> optv;
+    for (auto& s : opts) optv.push_back(s.c_str());
+    rc = n.CompileProgram(prog, (int) optv.size(), optv.data());
+    if (rc != 0) {
+        size_t ls = 0;
+        n.GetProgramLogSize(prog, &ls);
+        std::string log(ls + 1, '\0');
+        n.GetProgramLog(prog, &log[0]);
+        n.DestroyProgram(&prog);
+        return fail(AD4CL_ERR_COMPILE, "NVRTC build of '%s' failed:\n%s", entry, log.c_str());
+    }
+    size_t cs = 0;
+    n.GetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaFree(0)); /* make the primary context current for the driver API */
+    ad4cl_kernel* k = new_kernel(ctx, entry, signature);
+    CUresult r = driver().cuModuleLoadData(&k->module, cubin.data());
+    if (r != CUDA_SUCCESS) {
+        delete k;
+        return fail(AD4CL_ERR_CUDA, "cuModuleLoadData failed: %d", (int) r);
+    }
+    std::string fn = std::string(entry) + "__entry";
+    r = driver().cuModuleGetFunction(&k->function, k->module, fn.c_str());
+    if (r != CUDA_SUCCESS) {
+        driver().cuModuleUnload(k->module);
+        delete k;
+        return fail(AD4CL_ERR_CUDA, "cuModuleGetFunction(%s) failed: %d", fn.c_str(), (int) r);
+    }
+    k->cfg.reference_quirks = reference_quirks;
+    *out = k;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_free(ad4cl_kernel* k) {
+    if (!k) return AD4CL_OK;
+    cudaSetDevice(k->ctx->device);
+    cudaStreamSynchronize(k->ctx->stream);
+    k->release();
+    if (k->ev0) cudaEventDestroy(k->ev0);
+    if (k->ev1) cudaEventDestroy(k->ev1);
+    if (k->module && driver().cuModuleUnload) driver().cuModuleUnload(k->module);
+    delete k;
+    return AD4CL_OK;
+}
+
+const char* ad4cl_cuda_kernel_signature(ad4cl_kernel* k) { return k ? k->signature.c_str() : nullptr; }
+
+static int arg_at(ad4cl_kernel* k, int index, const char* kinds, Arg** a) {
+    if (!k) return fail(AD4CL_ERR_INVALID, "kernel is NULL");
+    if (index < 0 || index >= (int) k->args.size())
+        return fail(AD4CL_ERR_INVALID, "kernel %s has %zu parameters; index %d is out of range", k->name.c_str(), k->args.size(), index);
+    *a = &k->args[index];
+    if (strchr("GSO", (*a)->kind)) return 1; /* runtime-provided: accept and ignore */
+    if (!strchr(kinds, (*a)->kind))
+        return fail(AD4CL_ERR_INVALID, "kernel %s: parameter %d has kind '%c'", k->name.c_str(), index, (*a)->kind);
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_set_arg_buffer(ad4cl_kernel* k, int index, ad4cl_buffer* buf) {
+    Arg* a = nullptr;
+    int rc = arg_at(k, index, "VDI", &a);
+    if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
+    a->buf = buf;
+    a->first_id = -1;
+    a->set = buf != nullptr || a->kind != 'V';
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_set_arg_int(ad4cl_kernel* k, int index, int value) {
+    Arg* a = nullptr;
+    int rc = arg_at(k, index, "i", &a);
+    if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
+    a->ival = value;
+    a->set = true;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_set_arg_double(ad4cl_kernel* k, int index, double value) {
+    Arg* a = nullptr;
+    int rc = arg_at(k, index, "d", &a);
+    if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
+    a->dval = value;
+    a->set = true;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_set_arg_params(ad4cl_kernel* k, int index, int first_id, int count) {
+    Arg* a = nullptr;
+    int rc = arg_at(k, index, "V", &a);
+    if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
+    if (first_id < 0 || count < 1) return fail(AD4CL_ERR_INVALID, "bad independent range [%d,+%d)", first_id, count);
+    a->first_id = first_id;
+    a->count = count;
+    a->buf = nullptr;
+    a->set = true;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_config_default(ad4cl_kernel_config* cfg) {
+    if (!cfg) return fail(AD4CL_ERR_INVALID, "cfg is NULL");
+    memset(cfg, 0, sizeof *cfg);
+    cfg->global_size[1] = 1;
+    cfg->max_ops = 64;
+    cfg->far_plane = 1;
+    cfg->acc_mode = AD4CL_ACC_AUTO;
+    cfg->tape_tier = AD4CL_TAPE_AUTO;
+    cfg->epilogue = AD4CL_EPILOGUE_SUM;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_configure(ad4cl_kernel* k, const ad4cl_kernel_config* cfg) {
+    if (!k || !cfg) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (cfg->global_size[0] <= 0) return fail(AD4CL_ERR_INVALID, "global_size[0] must be positive");
+    if (cfg->max_ops <= 0) return fail(AD4CL_ERR_INVALID, "max_ops must be positive");
+    const int quirks = k->cfg.reference_quirks;
+    k->cfg = *cfg;
+    k->cfg.reference_quirks = quirks; /* fixed when the kernel was created */
+    k->configured = true;
+    k->ready = false;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_eval_device(ad4cl_kernel* k, const double* theta_dev, int nparams, double* result_dev,
+        int want_gradient, int apply_epilogue) {
+    if (!k || !result_dev || (!theta_dev && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    int rc = prepare(k, nparams);
+    if (rc != AD4CL_OK) return rc;
+    return enqueue(k, theta_dev, result_dev, want_gradient, apply_epilogue);
+}
+
+int ad4cl_cuda_check(ad4cl_kernel* k) {
+    if (!k) return fail(AD4CL_ERR_INVALID, "kernel is NULL");
+    if (!k->ready) return AD4CL_OK;
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(k->status_pinned, k->status_dev, sizeof (int), cudaMemcpyDeviceToHost, k->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(k->ctx->stream));
+    return status_to_error(k, *k->status_pinned);
+}
+
+int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f, double* grad) {
+    if (!k || !f || (!theta && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    int rc = prepare(k, nparams);
+    if (rc != AD4CL_OK) return rc;
+    cudaStream_t st = k->ctx->stream;
+    const int ncols = nparams + 3;
+    if (nparams > 0) {
+        memcpy(k->theta_pinned, theta, sizeof (double) * (size_t) nparams);
+        CUDA_TRY(cudaMemcpyAsync(k->theta_dev, k->theta_pinned, sizeof (double) * (size_t) nparams, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaEventRecord(k->ev0, st));
+    rc = enqueue(k, k->theta_dev, k->result_dev, grad != nullptr, 1);
+    if (rc != AD4CL_OK) return rc;
+    CUDA_TRY(cudaEventRecord(k->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(k->result_pinned, k->result_dev, sizeof (double) * (size_t) ncols, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(k->status_pinned, k->status_dev, sizeof (int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventElapsedTime(&k->stats.kernel_ms, k->ev0, k->ev1));
+    rc = status_to_error(k, *k->status_pinned);
+    if (rc != AD4CL_OK) return rc;
+    *f = k->result_pinned[nparams];
+    if (grad) memcpy(grad, k->result_pinned, sizeof (double) * (size_t) nparams);
+    k->stats.ops = k->result_pinned[nparams + 1];
+    k->stats.slots = k->result_pinned[nparams + 2];
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_last_stats(ad4cl_kernel* k, ad4cl_eval_stats* stats) {
+    if (!k || !stats) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    *stats = k->stats;
+    return AD4CL_OK;
+}
+
+} // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,270 @@
+"""Python host side of the CUDA AD runtime: a thin ctypes mirror of the C ABI
+(include/ad4cl_cuda.h), shaped like the host protocol every AD4CL example
+follows (test/admb/simple.cpp:111-268 set-up, :270-384 one evaluation):
+
+    ctx    = Context(device)                       # platform / context / queue
+    x_d    = ctx.buffer(x); y_d = ctx.buffer(y)    # cl::Buffer + enqueueWriteBuffer
+    kernel = ctx.builtin("linreg2_p")              # program build + cl::Kernel
+    kernel.set_args(None, None, params(0), params(1), x_d, y_d, None, n)   # setArg 0..7
+    kernel.configure(global_size=n, max_ops=4, epilogue="half_n_log")
+    f, grad = kernel.eval([a, b])                  # the whole of userfunction()
+
+There is NO CPU fallback: importing this module loads libad4cl_cuda.so and
+raises if it is missing; creating a Context raises without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libad4cl_cuda.so")
+
+OK, ERR_CUDA, ERR_INVALID, ERR_TAPE_OVERFLOW, ERR_WINDOW, ERR_COMPILE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+ACC = {"auto": -1, "thread": 0, "warp": 1, "global": 2}
+TAPE = {"auto": -1, "hbm": 0, "shared": 1}
+EPILOGUE = {"sum": 0, "half_n_log": 1}
+
+
+class Ad4clError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"ad4cl_cuda error {code}: {message}")
+        self.code = code
+
+
+class KernelConfig(ctypes.Structure):
+    _fields_ = [("global_size", c_longlong * 2), ("local_size", c_int * 2), ("max_ops", c_int),
+                ("max_slots", c_int), ("window", c_int), ("far_plane", c_int), ("acc_mode", c_int),
+                ("tape_tier", c_int), ("epilogue", c_int), ("epilogue_n", c_double),
+                ("blocks_per_sm", c_int), ("reference_quirks", c_int)]
+
+
+class EvalStats(ctypes.Structure):
+    _fields_ = [("ops", c_double), ("slots", c_double), ("grid", c_int), ("block", c_int),
+                ("smem_bytes", c_size_t), ("arena_bytes", c_size_t), ("kernel_ms", c_float)]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C ad4cl_b200/csrc` (or __graft_entry__.build()). "
+            "ad4cl_b200 has no CPU implementation to fall back to.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.ad4cl_cuda_last_error.restype = c_char_p
+    lib.ad4cl_cuda_stream.restype = c_void_p
+    lib.ad4cl_cuda_stream.argtypes = [c_void_p]
+    lib.ad4cl_cuda_use_stream.argtypes = [c_void_p, c_void_p]
+    lib.ad4cl_cuda_buffer_device_ptr.restype = c_void_p
+    lib.ad4cl_cuda_buffer_device_ptr.argtypes = [c_void_p]
+    lib.ad4cl_cuda_builtin_name.restype = c_char_p
+    lib.ad4cl_cuda_builtin_signature.restype = c_char_p
+    lib.ad4cl_cuda_kernel_signature.restype = c_char_p
+    lib.ad4cl_cuda_kernel_signature.argtypes = [c_void_p]
+    lib.ad4cl_cuda_init.argtypes = [c_int, POINTER(c_void_p)]
+    lib.ad4cl_cuda_shutdown.argtypes = [c_void_p]
+    lib.ad4cl_cuda_device_sm_count.argtypes = [c_void_p]
+    lib.ad4cl_cuda_buffer_create.argtypes = [c_void_p, c_size_t, POINTER(c_void_p)]
+    lib.ad4cl_cuda_buffer_wrap.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(c_void_p)]
+    lib.ad4cl_cuda_buffer_upload.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t]
+    lib.ad4cl_cuda_buffer_download.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t]
+    lib.ad4cl_cuda_buffer_free.argtypes = [c_void_p]
+    lib.ad4cl_cuda_kernel_builtin.argtypes = [c_void_p, c_char_p, c_int, POINTER(c_void_p)]
+    lib.ad4cl_cuda_kernel_from_source.argtypes = [c_void_p, c_char_p, c_char_p, c_char_p, c_char_p, c_int,
+                                                  POINTER(c_void_p)]
+    lib.ad4cl_cuda_kernel_free.argtypes = [c_void_p]
+    lib.ad4cl_cuda_kernel_set_arg_buffer.argtypes = [c_void_p, c_int, c_void_p]
+    lib.ad4cl_cuda_kernel_set_arg_int.argtypes = [c_void_p, c_int, c_int]
+    lib.ad4cl_cuda_kernel_set_arg_double.argtypes = [c_void_p, c_int, c_double]
+    lib.ad4cl_cuda_kernel_set_arg_params.argtypes = [c_void_p, c_int, c_int, c_int]
+    lib.ad4cl_cuda_kernel_config_default.argtypes = [POINTER(KernelConfig)]
+    lib.ad4cl_cuda_kernel_configure.argtypes = [c_void_p, POINTER(KernelConfig)]
+    lib.ad4cl_cuda_eval.argtypes = [c_void_p, c_void_p, c_int, POINTER(c_double), c_void_p]
+    lib.ad4cl_cuda_eval_device.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int]
+    lib.ad4cl_cuda_check.argtypes = [c_void_p]
+    lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != OK:
+        raise Ad4clError(rc, (lib.ad4cl_cuda_last_error() or b"").decode(errors="replace"))
+
+
+def builtin_kernels() -> dict[str, str]:
+    """name -> signature of the kernels compiled into the library."""
+    return {lib.ad4cl_cuda_builtin_name(i).decode(): lib.ad4cl_cuda_builtin_signature(i).decode()
+            for i in range(lib.ad4cl_cuda_builtin_count())}
+
+
+class params:
+    """Marks a kernel argument bound to `count` independents starting at id `first_id`
+    (what ad_init_var + enqueueWriteBuffer(a_d, ...) set up in simple.cpp:278-286)."""
+
+    def __init__(self, first_id: int, count: int = 1):
+        self.first_id, self.count = first_id, count
+
+
+class Buffer:
+    def __init__(self, ctx: "Context", handle: c_void_p, nbytes: int):
+        self.ctx, self._h, self.nbytes = ctx, handle, nbytes
+
+    @property
+    def device_ptr(self) -> int:
+        return lib.ad4cl_cuda_buffer_device_ptr(self._h)
+
+    def upload(self, host: np.ndarray, offset: int = 0) -> None:
+        host = np.ascontiguousarray(host)
+        _check(lib.ad4cl_cuda_buffer_upload(self._h, offset, host.ctypes.data, host.nbytes))
+
+    def download(self, dtype=np.float64, count: int | None = None, offset: int = 0) -> np.ndarray:
+        dt = np.dtype(dtype)
+        n = (self.nbytes - offset) // dt.itemsize if count is None else count
+        out = np.empty(n, dtype=dt)
+        _check(lib.ad4cl_cuda_buffer_download(self._h, offset, out.ctypes.data, out.nbytes))
+        return out
+
+    def free(self) -> None:
+        if self._h:
+            lib.ad4cl_cuda_buffer_free(self._h)
+            self._h = None
+
+
+class Kernel:
+    def __init__(self, ctx: "Context", handle: c_void_p, name: str):
+        self.ctx, self._h, self.name = ctx, handle, name
+        self.signature = lib.ad4cl_cuda_kernel_signature(handle).decode()
+        self._keep = []
+
+    def set_arg(self, index: int, value) -> None:
+        """cl::Kernel::setArg: Buffer, params(...), int, float; None for gs / stack / out."""
+        kind = self.signature[index] if 0 <= index < len(self.signature) else "?"
+        if value is None:
+            if kind in "GSO":
+                return
+            if kind in "DI":
+                _check(lib.ad4cl_cuda_kernel_set_arg_buffer(self._h, index, None))
+                return
+            raise Ad4clError(ERR_INVALID, f"argument {index} of {self.name} (kind {kind}) cannot be None")
+        if isinstance(value, params):
+            _check(lib.ad4cl_cuda_kernel_set_arg_params(self._h, index, value.first_id, value.count))
+        elif isinstance(value, Buffer):
+            self._keep.append(value)
+            _check(lib.ad4cl_cuda_kernel_set_arg_buffer(self._h, index, value._h))
+        elif isinstance(value, (int, np.integer)):
+            _check(lib.ad4cl_cuda_kernel_set_arg_int(self._h, index, int(value)))
+        elif isinstance(value, (float, np.floating)):
+            _check(lib.ad4cl_cuda_kernel_set_arg_double(self._h, index, float(value)))
+        else:
+            raise TypeError(f"unsupported kernel argument {value!r}")
+
+    def set_args(self, *values) -> "Kernel":
+        if len(values) != len(self.signature):
+            raise Ad4clError(ERR_INVALID, f"{self.name} takes {len(self.signature)} arguments ({self.signature}), got {len(values)}")
+        for i, v in enumerate(values):
+            self.set_arg(i, v)
+        return self
+
+    def configure(self, global_size, max_ops: int, *, local_size=None, max_slots: int = 0, window: int = 0,
+                  far_plane: bool = True, acc: str = "auto", tape: str = "auto", epilogue: str = "sum",
+                  epilogue_n: float = 0.0, blocks_per_sm: int = 0) -> "Kernel":
+        cfg = KernelConfig()
+        _check(lib.ad4cl_cuda_kernel_config_default(byref(cfg)))
+        gs = (global_size, 1) if np.isscalar(global_size) else tuple(global_size)
+        cfg.global_size[0], cfg.global_size[1] = int(gs[0]), int(gs[1]) if len(gs) > 1 else 1
+        if local_size is not None:
+            ls = (local_size, 1) if np.isscalar(local_size) else tuple(local_size)
+            cfg.local_size[0], cfg.local_size[1] = int(ls[0]), int(ls[1]) if len(ls) > 1 else 1
+        cfg.max_ops, cfg.max_slots, cfg.window = int(max_ops), int(max_slots), int(window)
+        cfg.far_plane = 1 if far_plane else 0
+        cfg.acc_mode, cfg.tape_tier, cfg.epilogue = ACC[acc], TAPE[tape], EPILOGUE[epilogue]
+        cfg.epilogue_n = float(epilogue_n)
+        cfg.blocks_per_sm = int(blocks_per_sm)
+        _check(lib.ad4cl_cuda_kernel_configure(self._h, byref(cfg)))
+        return self
+
+    def eval(self, theta, want_grad: bool = True):
+        """theta (host) -> (f, grad[P]) on the host; grad is None when want_grad is False."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        f = c_double()
+        g = np.empty(len(th)) if want_grad else None
+        _check(lib.ad4cl_cuda_eval(self._h, th.ctypes.data, len(th), byref(f), g.ctypes.data if want_grad else None))
+        return f.value, g
+
+    def eval_device(self, theta_dev_ptr: int, nparams: int, result_dev_ptr: int, *, want_grad: bool = True,
+                    apply_epilogue: bool = True) -> None:
+        """Asynchronous evaluation on the context's stream with device-resident theta and
+        result ([grad..., f, ops, slots], nparams + 3 doubles)."""
+        _check(lib.ad4cl_cuda_eval_device(self._h, theta_dev_ptr, nparams, result_dev_ptr,
+                                          1 if want_grad else 0, 1 if apply_epilogue else 0))
+
+    def check(self) -> None:
+        _check(lib.ad4cl_cuda_check(self._h))
+
+    def stats(self) -> dict:
+        s = EvalStats()
+        _check(lib.ad4cl_cuda_last_stats(self._h, byref(s)))
+        return {"ops": s.ops, "slots": s.slots, "grid": s.grid, "block": s.block, "smem_bytes": s.smem_bytes,
+                "arena_bytes": s.arena_bytes, "kernel_ms": s.kernel_ms}
+
+    def free(self) -> None:
+        if self._h:
+            lib.ad4cl_cuda_kernel_free(self._h)
+            self._h = None
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_init(device, byref(h)))
+        self._h, self.device = h, device
+
+    @property
+    def sm_count(self) -> int:
+        return lib.ad4cl_cuda_device_sm_count(self._h)
+
+    @property
+    def stream(self) -> int:
+        return lib.ad4cl_cuda_stream(self._h)
+
+    def use_stream(self, cuda_stream: int | None) -> None:
+        _check(lib.ad4cl_cuda_use_stream(self._h, cuda_stream))
+
+    def buffer(self, data=None, nbytes: int | None = None) -> Buffer:
+        """cl::Buffer (+ blocking enqueueWriteBuffer when `data` is given)."""
+        if data is not None:
+            data = np.ascontiguousarray(data)
+            nbytes = data.nbytes
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_buffer_create(self._h, nbytes, byref(h)))
+        b = Buffer(self, h, nbytes)
+        if data is not None and nbytes:
+            b.upload(data)
+        return b
+
+    def wrap(self, device_ptr: int, nbytes: int) -> Buffer:
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_buffer_wrap(self._h, device_ptr, nbytes, byref(h)))
+        return Buffer(self, h, nbytes)
+
+    def builtin(self, name: str, quirks: bool = False) -> Kernel:
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_kernel_builtin(self._h, name.encode(), 1 if quirks else 0, byref(h)))
+        return Kernel(self, h, name)
+
+    def from_source(self, source: str, entry: str, signature: str, options: str = "", quirks: bool = False) -> Kernel:
+        """JIT path (NVRTC), the analogue of cl::Program(context, ad.cl + kernel text).build()."""
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_kernel_from_source(self._h, source.encode(), entry.encode(), signature.encode(),
+                                                 options.encode() if options else None, 1 if quirks else 0, byref(h)))
+        return Kernel(self, h, entry)
+
+    def close(self) -> None:
+        if self._h:
+            lib.ad4cl_cuda_shutdown(self._h)
+            self._h = None

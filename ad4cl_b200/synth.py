@@ -157,38 +157,6 @@ def catch_at_age(n: int, start: int = 0, count: int | None = None):
     return obs, theta0, R
 
 
-def caa_ops_per_item(n: int) -> tuple[int, int]:
-    """(total AD ops, total operand slots) of one catch_at_age evaluation with n
-    observations; counted from the kernel text (objectives.cl), see DESIGN.md."""
-    R = n // (CAA_YEARS * CAA_AGES)
-    ops = slots = 0
-    for age in range(CAA_AGES):
-        for year in range(CAA_YEARS):
-            o = s = 1                        # M = exp(logM)            k=1
-            have = False
-            for kk in range(age + 1):
-                yy = year - age + kk
-                if yy >= 0:
-                    # minus_dv(1) times(2) times_vd(1) exp(1) plus_vd(1) divide_dv(1) exp(1) times(2) plus(2)
-                    o += 9
-                    s += 12
-                if kk < age:
-                    if have:
-                        o += 1
-                        s += 2
-                    have = True
-            if have:
-                o += 1
-                s += 2                      # logN = minus(theta, cumZ)
-            # exp(1) | times_vd exp minus_dv (3) | plus(2) exp(1) | divide(2) times*3(6) | log(1) minus_dv(1)
-            # | exp(1) times(2) times_vd(1) | times(2) divide(2) plus(2)
-            o += 1 + 3 + 2 + 4 + 2 + 3 + 3
-            s += 1 + 3 + 3 + 8 + 2 + 4 + 6
-            ops += o * R
-            slots += s * R
-    return ops, slots
-
-
 # --------------------------------------------------------------------------- config 5
 def tape_stress(n: int, start: int = 0, count: int | None = None):
     """x ~ U(0.5, 1.5) seed 6; theta = 1 (P = 10)."""

@@ -1,0 +1,151 @@
+"""The BASELINE.json configurations as (data, kernel arguments, tape budget) recipes.
+
+`describe(name, n, ...)` produces host-side inputs only (numpy; usable on a CPU
+box, by the oracle and by the tests); `bind(ctx, desc)` uploads them and returns
+a configured `host.Kernel`.  Nothing here computes an objective.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import synth
+
+
+@dataclass
+class Workload:
+    name: str                 # workload key
+    kernel: str               # kernel name (objectives.cl / matrix.cl)
+    theta: np.ndarray         # evaluation point, P doubles
+    d0: np.ndarray | None
+    d1: np.ndarray | None
+    size: int                 # data work-items (this shard)
+    i0: int = 0
+    i1: int = 0
+    epilogue: str = "sum"
+    epilogue_n: float = 0.0   # n of the epilogue when it is not `size` (sharded runs)
+    max_ops: int = 64         # per work-item
+    max_slots: int = 0
+    ops_total: int = 0        # per evaluation, for the roofline arithmetic
+    slots_total: int = 0
+    input_bytes: int = 0      # data bytes read once per evaluation
+    linreg2: bool = False     # (a, b) passed as two separate V arguments (simple.cl signature)
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def nparams(self) -> int:
+        return len(self.theta)
+
+    def algorithmic_bytes(self) -> int:
+        """24 B per operand slot (12 written forward + 12 read in
+        reverse) + inputs read once + 8 (P+1) out."""
+        return 24 * self.slots_total + self.input_bytes + 8 * (self.nparams + 1)
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous observation shard [start, start+count) of rank `rank`."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 33, p: int = 10) -> Workload:
+    start, count = shard_range(n, rank, world)
+    if name in ("linreg2_main", "linreg2_simple"):
+        gen = synth.main_cpp_recipe if name == "linreg2_main" else synth.simple_cpp_recipe
+        x, y, (a, b) = gen(n, start, count)
+        return Workload(name, "linreg2_p", np.array([a, b]), x, y, count, epilogue="half_n_log", epilogue_n=n,
+                        max_ops=4, max_slots=6, ops_total=4 * count, slots_total=6 * count,
+                        input_bytes=16 * count, linreg2=True)
+    if name in ("regression_linear", "regression_logistic"):
+        kind = name.split("_")[1]
+        X, y, beta = synth.regression(n, p, kind, start, count)
+        ops = (2 * p + 1) if kind == "linear" else (2 * p + 4)
+        slots = (3 * p + 1) if kind == "linear" else (3 * p + 5)
+        return Workload(name, name, beta, X, y, count, i0=p,
+                        epilogue="half_n_log" if kind == "linear" else "sum", epilogue_n=n,
+                        max_ops=ops, max_slots=slots, ops_total=ops * count, slots_total=slots * count,
+                        input_bytes=8 * (p + 1) * count)
+    if name == "catch_at_age":
+        obs, theta0, R = synth.catch_at_age(n, start, count)
+        ops, slots = caa_totals(n, start, count)
+        return Workload(name, name, theta0, obs, None, count, i0=R, i1=start, max_ops=128, max_slots=176,
+                        ops_total=ops, slots_total=slots, input_bytes=8 * count)
+    if name == "tape_stress":
+        x, theta = synth.tape_stress(n, start, count)
+        theta = np.ones(p)
+        ops, slots = 3 * steps + 1, 4 * steps + 1
+        return Workload(name, name, theta, x, None, count, i0=steps, i1=p, max_ops=ops, max_slots=slots,
+                        ops_total=ops * count, slots_total=slots * count, input_bytes=8 * count,
+                        extra={"steps": steps})
+    if name == "op_zoo":
+        d0, theta = synth.op_zoo(n)
+        return Workload(name, name, theta, d0[start:start + count], None, count, max_ops=48, max_slots=64,
+                        ops_total=43 * count, slots_total=0, input_bytes=8 * count)
+    raise KeyError(name)
+
+
+def caa_totals(n: int, start: int, count: int) -> tuple[int, int]:
+    """AD operators and operand slots of catch_at_age over observations [start, start+count)."""
+    R = n // (synth.CAA_YEARS * synth.CAA_AGES)
+    per_cell = _caa_per_cell()
+    ops = slots = 0
+    first_cell, last_cell = start // R, (start + count - 1) // R
+    for cell in range(first_cell, last_cell + 1):
+        lo, hi = max(start, cell * R), min(start + count, (cell + 1) * R)
+        o, s = per_cell[cell]
+        ops += o * (hi - lo)
+        slots += s * (hi - lo)
+    return ops, slots
+
+
+_CAA_CACHE: list | None = None
+
+
+def _caa_per_cell():
+    """(ops, slots) one work-item of cell = year + 40*age records; counted from the
+    kernel text of catch_at_age (objectives.cl) -- checked against the device's own
+    counters in tests/test_gpu_parity.py."""
+    global _CAA_CACHE
+    if _CAA_CACHE is None:
+        out = []
+        for age in range(synth.CAA_AGES):
+            for year in range(synth.CAA_YEARS):
+                o = s = 1
+                have = False
+                for kk in range(age + 1):
+                    if year - age + kk >= 0:
+                        o += 9
+                        s += 12
+                    if kk < age:
+                        if have:
+                            o += 1
+                            s += 2
+                        have = True
+                if have:
+                    o += 1
+                    s += 2
+                o += 18
+                s += 27
+                out.append((o, s))
+        # cell index = year + 40*age: the loops above ran age-major, year-minor
+        _CAA_CACHE = out
+    return _CAA_CACHE
+
+
+def bind(ctx, w: Workload, *, quirks: bool = False, **cfg):
+    """Upload the workload's data and return a configured kernel."""
+    from . import host
+    k = ctx.builtin(w.kernel, quirks=quirks)
+    d0 = ctx.buffer(w.d0) if w.d0 is not None else None
+    d1 = ctx.buffer(w.d1) if w.d1 is not None else None
+    if w.linreg2:
+        k.set_args(None, None, host.params(0), host.params(1), d0, d1, None, w.size)
+    else:
+        k.set_args(None, None, host.params(0, w.nparams), d0, d1, None, w.size, w.i0, w.i1)
+    opts = dict(max_ops=w.max_ops, max_slots=w.max_slots, epilogue=w.epilogue, epilogue_n=w.epilogue_n)
+    opts.update(cfg)
+    k.configure(max(w.size, 1), **opts)
+    k._buffers = (d0, d1)
+    return k

@@ -1,0 +1,177 @@
+/*
+ * ad4cl_cuda.h -- C ABI of libad4cl_cuda.so, the B200 (sm_100a) replacement for
+ * the OpenCL plumbing + host adjoint sweep that every AD4CL example hand-writes
+ * around a launch.  Plain C: opaque handles, pointers and sizes only.
+ *
+ * Reference interface each entry point replaces (paths under the AD4CL tree):
+ *
+ *   ad4cl_cuda_init / _shutdown        platform, context, queue set-up
+ *                                      test/admb/simple.cpp:111-200, main.cpp:159-250
+ *   ad4cl_cuda_kernel_builtin          cl::Program build of ad.cl + user file, cl::Kernel
+ *   ad4cl_cuda_kernel_from_source      test/admb/simple.cpp:138-175, 232  (NVRTC here)
+ *   ad4cl_cuda_buffer_*                cl::Buffer + enqueueWrite/ReadBuffer
+ *                                      test/admb/simple.cpp:206-230, 283-286
+ *   ad4cl_cuda_kernel_set_arg_*        cl::Kernel::setArg, test/admb/simple.cpp:240-262,
+ *                                      test/matrix/matrix_mul.cpp:184-192
+ *   ad4cl_cuda_kernel_configure        global/local size, stack size
+ *                                      test/admb/simple.cpp:235-238, simple.dat:6
+ *   ad4cl_cuda_eval                    ONE objective+gradient evaluation, i.e. the whole of
+ *                                      test/admb/simple.cpp:283-384: write gs/params ->
+ *                                      enqueueNDRangeKernel -> read gs, stack, out ->
+ *                                      gpu_restore (ad4cl.h:83-87) -> host sum of out[]
+ *                                      (simple.cpp:357-361) -> epilogue (simple.cpp:365) ->
+ *                                      compute_gradient (ad4cl.h:775-802) -> g[param.id]
+ *   ad4cl_cuda_eval_device             same, parameters and result stay in device memory
+ *                                      (multi-GPU drivers all-reduce the result in place)
+ *   ad4cl_cuda_last_error              cl::Error::what() + build log, simple.cpp:264-266
+ *
+ * Every function returns AD4CL_OK (0) or a negative AD4CL_ERR_* code; the text
+ * of the last failure on the calling thread is ad4cl_cuda_last_error().  There
+ * is no CPU fallback: without a CUDA device ad4cl_cuda_init fails.
+ *
+ * Threading: calls on one context must be serialised by the caller (the
+ * reference's host API is single-threaded, ad4cl.h:28-32); distinct contexts
+ * are independent.
+ */
+#ifndef AD4CL_CUDA_H
+#define AD4CL_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ad4cl_context ad4cl_context;
+typedef struct ad4cl_kernel ad4cl_kernel;
+typedef struct ad4cl_buffer ad4cl_buffer;
+
+enum {
+    AD4CL_OK = 0,
+    AD4CL_ERR_CUDA = -1,          /* a CUDA runtime / driver call failed */
+    AD4CL_ERR_INVALID = -2,       /* bad argument, unknown kernel, unset kernel argument */
+    AD4CL_ERR_TAPE_OVERFLOW = -3, /* a work-item recorded more than the configured tape holds */
+    AD4CL_ERR_WINDOW = -4,        /* far operand met with the far-adjoint plane disabled */
+    AD4CL_ERR_COMPILE = -5,       /* NVRTC rejected the source; the log is in last_error */
+    AD4CL_ERR_NOMEM = -6
+};
+
+/* where the adjoints of the independents are accumulated during the sweep */
+enum {
+    AD4CL_ACC_AUTO = -1,
+    AD4CL_ACC_THREAD = 0,   /* per-thread shared-memory accumulators + block tree */
+    AD4CL_ACC_WARP = 1,     /* warp-shuffle reduction per contribution */
+    AD4CL_ACC_GLOBAL = 2    /* fp64 atomics into a gradient array (many independents) */
+};
+
+/* tape tier */
+enum {
+    AD4CL_TAPE_AUTO = -1,
+    AD4CL_TAPE_HBM = 0,     /* thread-interleaved arena in HBM (L2-resident when small) */
+    AD4CL_TAPE_SHARED = 1   /* rows in shared memory (short tapes) */
+};
+
+/* scalar epilogue applied to S = sum_i out_i */
+enum {
+    AD4CL_EPILOGUE_SUM = 0,      /* f = S */
+    AD4CL_EPILOGUE_HALF_N_LOG = 1 /* f = (n/2) log S      (simple.cpp:365, main.cpp:417) */
+};
+
+typedef struct ad4cl_kernel_config {
+    long long global_size[2];  /* NDRange; global_size[1] = 1 for 1-D */
+    int local_size[2];         /* work-group; product <= 256; {0,0} = runtime's choice */
+    int max_ops;               /* most AD operators one work-item records */
+    int max_slots;             /* most operand slots (sum of k) one work-item records; 0 = 2*max_ops */
+    int window;                /* adjoint ring entries (power of two); 0 = runtime's choice */
+    int far_plane;             /* 1: allow operands older than `window` operators (default 1) */
+    int acc_mode;              /* AD4CL_ACC_* */
+    int tape_tier;             /* AD4CL_TAPE_* */
+    int epilogue;              /* AD4CL_EPILOGUE_* */
+    double epilogue_n;         /* n of the epilogue; 0 = number of data work-items */
+    int blocks_per_sm;         /* persistent grid = SMs x this; 0 = occupancy maximum */
+    int reference_quirks;      /* builtin kernels only: 1 = reference arithmetic as written */
+} ad4cl_kernel_config;
+
+typedef struct ad4cl_eval_stats {
+    double ops;             /* AD operators recorded by the evaluation */
+    double slots;           /* operand slots recorded (12 B each, written once, read once) */
+    int grid, block;        /* launch shape used */
+    size_t smem_bytes;
+    size_t arena_bytes;
+    float kernel_ms;        /* device time of the last evaluation (both launches) */
+} ad4cl_eval_stats;
+
+int ad4cl_cuda_init(int device, ad4cl_context** ctx);
+int ad4cl_cuda_shutdown(ad4cl_context* ctx);
+const char* ad4cl_cuda_last_error(void);
+/* the CUDA stream of the context, as a cudaStream_t cast to void* */
+void* ad4cl_cuda_stream(ad4cl_context* ctx);
+/* run on a caller-owned stream (e.g. torch's current stream); NULL restores the context's own */
+int ad4cl_cuda_use_stream(ad4cl_context* ctx, void* cuda_stream);
+int ad4cl_cuda_device_sm_count(ad4cl_context* ctx);
+
+int ad4cl_cuda_buffer_create(ad4cl_context* ctx, size_t bytes, ad4cl_buffer** buf);
+/* wrap caller-owned device memory (never freed by the library) */
+int ad4cl_cuda_buffer_wrap(ad4cl_context* ctx, void* device_ptr, size_t bytes, ad4cl_buffer** buf);
+int ad4cl_cuda_buffer_upload(ad4cl_buffer* buf, size_t offset, const void* host, size_t bytes);
+int ad4cl_cuda_buffer_download(ad4cl_buffer* buf, size_t offset, void* host, size_t bytes);
+void* ad4cl_cuda_buffer_device_ptr(ad4cl_buffer* buf);
+int ad4cl_cuda_buffer_free(ad4cl_buffer* buf);
+
+/* a kernel compiled ahead of time into the library (ad4cl_b200/kernels/\*.cl) */
+int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int reference_quirks,
+        ad4cl_kernel** kernel);
+/* number of built-in kernels; name/signature of the i-th */
+int ad4cl_cuda_builtin_count(void);
+const char* ad4cl_cuda_builtin_name(int i);
+const char* ad4cl_cuda_builtin_signature(int i);
+/*
+ * Compile `source` (OpenCL-C-dialect kernel text written against ad.cl) with
+ * NVRTC for sm_100a.  `signature` gives the kinds of `entry`'s parameters in
+ * order:  G gs  S gradient_stack  O out  V ad_variable*  D double*  I int*
+ * i int  d double   (e.g. "GSVVDDOi" for test/admb/simple.cl).  `options` is a
+ * space-separated list of extra compiler options (may be NULL).
+ */
+int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const char* entry,
+        const char* signature, const char* options, int reference_quirks, ad4cl_kernel** kernel);
+int ad4cl_cuda_kernel_free(ad4cl_kernel* kernel);
+const char* ad4cl_cuda_kernel_signature(ad4cl_kernel* kernel);
+
+/* arguments are indexed like the user kernel's parameter list (cl::Kernel::setArg);
+   G, S and O positions accept any value and ignore it */
+int ad4cl_cuda_kernel_set_arg_buffer(ad4cl_kernel* kernel, int index, ad4cl_buffer* buf);
+int ad4cl_cuda_kernel_set_arg_int(ad4cl_kernel* kernel, int index, int value);
+int ad4cl_cuda_kernel_set_arg_double(ad4cl_kernel* kernel, int index, double value);
+/* bind a V argument to `count` consecutive independents starting at id `first_id`;
+   ad4cl_cuda_eval fills them from theta[first_id .. first_id+count) */
+int ad4cl_cuda_kernel_set_arg_params(ad4cl_kernel* kernel, int index, int first_id, int count);
+
+int ad4cl_cuda_kernel_config_default(ad4cl_kernel_config* cfg);
+int ad4cl_cuda_kernel_configure(ad4cl_kernel* kernel, const ad4cl_kernel_config* cfg);
+
+/*
+ * One evaluation.  theta: nparams doubles (host).  On return *f is the
+ * objective and grad[0..nparams) its gradient (grad may be NULL: objective
+ * only, nothing is recorded).  Crossing PCIe: 8*nparams bytes in,
+ * 8*(nparams+3) bytes out.
+ */
+int ad4cl_cuda_eval(ad4cl_kernel* kernel, const double* theta, int nparams, double* f, double* grad);
+/*
+ * Same with device-resident parameters and result, asynchronous on the
+ * context's stream: theta_dev holds nparams doubles; result_dev receives
+ * nparams+3 doubles [grad..., S_or_f, ops, slots].  With apply_epilogue = 0 the
+ * raw sums are left (so partial results of several devices can be added before
+ * the epilogue is applied).  Errors raised by the launch itself surface at the
+ * next ad4cl_cuda_check().
+ */
+int ad4cl_cuda_eval_device(ad4cl_kernel* kernel, const double* theta_dev, int nparams,
+        double* result_dev, int want_gradient, int apply_epilogue);
+/* synchronise the stream and report tape overflow / window errors of queued evaluations */
+int ad4cl_cuda_check(ad4cl_kernel* kernel);
+int ad4cl_cuda_last_stats(ad4cl_kernel* kernel, ad4cl_eval_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* AD4CL_CUDA_H */

@@ -1,0 +1,119 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerance: 1e-12 relative on the objective and on every gradient
+component (BASELINE.json north_star), the latter measured against the scale of
+the gradient, max(|g_ref|_inf, |g_ref_i|), because individual components may sit
+near a zero crossing (error metric)."""
+import numpy as np
+import pytest
+
+from ad4cl_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel_err(x, ref):
+    x, ref = np.atleast_1d(x), np.atleast_1d(ref)
+    scale = np.maximum(np.abs(ref), np.abs(ref).max())
+    return float(np.max(np.abs(x - ref) / np.maximum(scale, 1e-300)))
+
+
+def oracle_eval(O, w, quirks):
+    orc = O.best(quirks)
+    epi = 1 if w.epilogue == "half_n_log" else 0
+    name = w.kernel
+    return orc.eval_objective(name, w.theta, w.d0, w.d1, w.size, w.i0, w.i1, epilogue=epi,
+                              ops_per_item=w.max_ops), orc.kind
+
+
+CASES = [
+    ("linreg2_main", 1000, {}),
+    ("linreg2_main", 100003, {}),
+    ("linreg2_simple", 5003, {}),
+    ("regression_linear", 3001, {}),
+    ("regression_logistic", 3001, {}),
+    ("catch_at_age", 8000, {}),
+    ("tape_stress", 777, {"steps": 33}),
+    ("tape_stress", 777, {"steps": 200}),
+    ("op_zoo", 513, {}),
+]
+
+
+@pytest.mark.parametrize("quirks", [False, True], ids=["fixed", "quirks"])
+@pytest.mark.parametrize("name,n,kw", CASES, ids=[f"{c[0]}-{c[1]}" + ("-%d" % c[2]["steps"] if c[2] else "") for c in CASES])
+def test_objective_and_gradient_match_oracle(ctx, oracle_api, name, n, kw, quirks):
+    w = W.describe(name, n, **kw)
+    ref, kind = oracle_eval(oracle_api, w, quirks)
+    k = W.bind(ctx, w, quirks=quirks)
+    try:
+        f, g = k.eval(w.theta)
+        st = k.stats()
+    finally:
+        k.free()
+    assert rel_err(f, ref["f"]) <= RTOL, (f, ref["f"], kind)
+    assert rel_err(g, ref["grad"]) <= RTOL, (g, ref["grad"], kind)
+    # every operator of the reference's tape was recorded: entries = ops + n sum entries (+2 epilogue)
+    extra = w.size + (2 if w.epilogue == "half_n_log" else 0)
+    assert int(st["ops"]) == ref["entries"] - extra
+    if w.slots_total:
+        assert int(st["slots"]) == w.slots_total
+        assert int(st["ops"]) == w.ops_total
+
+
+@pytest.mark.parametrize("acc", ["thread", "warp", "global"])
+@pytest.mark.parametrize("tape", ["hbm", "shared"])
+def test_accumulator_modes_and_tape_tiers_agree(ctx, oracle_api, acc, tape):
+    w = W.describe("regression_logistic", 4099)
+    ref, _ = oracle_eval(oracle_api, w, False)
+    k = W.bind(ctx, w, acc=acc, tape=tape, local_size=64 if tape == "shared" else None)
+    try:
+        f, g = k.eval(w.theta)
+    finally:
+        k.free()
+    assert rel_err(f, ref["f"]) <= RTOL
+    assert rel_err(g, ref["grad"]) <= RTOL
+
+
+@pytest.mark.parametrize("window,far", [(4, True), (16, True), (128, False)])
+def test_far_operands(ctx, oracle_api, window, far):
+    """catch_at_age re-uses M = exp(log M) up to ~110 operators later: with a small
+    ring those operands go through the far-adjoint plane."""
+    w = W.describe("catch_at_age", 4000)
+    ref, _ = oracle_eval(oracle_api, w, False)
+    k = W.bind(ctx, w, window=window, far_plane=far)
+    try:
+        f, g = k.eval(w.theta)
+        f2, g2 = k.eval(w.theta)   # the arena (far bitmap) must be left clean
+    finally:
+        k.free()
+    assert rel_err(f, ref["f"]) <= RTOL
+    assert rel_err(g, ref["grad"]) <= RTOL
+    assert f2 == f and np.array_equal(g, g2), "evaluation is not bit-reproducible"
+
+
+def test_errors_are_reported_not_silent(ctx):
+    from ad4cl_b200 import host
+    w = W.describe("catch_at_age", 4000)
+    k = W.bind(ctx, w, max_ops=20, max_slots=30)
+    with pytest.raises(host.Ad4clError) as e:
+        k.eval(w.theta)
+    assert e.value.code == host.ERR_TAPE_OVERFLOW
+    k.free()
+    k = W.bind(ctx, w, window=8, far_plane=False)
+    with pytest.raises(host.Ad4clError) as e:
+        k.eval(w.theta)
+    assert e.value.code == host.ERR_WINDOW
+    k.free()
+    with pytest.raises(host.Ad4clError):
+        ctx.builtin("no_such_kernel")
+
+
+def test_objective_only(ctx, oracle_api):
+    w = W.describe("regression_linear", 3001)
+    ref, _ = oracle_eval(oracle_api, w, False)
+    k = W.bind(ctx, w)
+    f, g = k.eval(w.theta, want_grad=False)
+    assert g is None and rel_err(f, ref["f"]) <= RTOL
+    assert k.stats()["ops"] == 0
+    k.free()
