@@ -194,6 +194,12 @@ struct ad4cl_kernel {
     int* status_pinned = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ad4cl_eval_stats stats{};
+    /* opt-in timing of the fused kernel alone (ad4cl_cuda_kernel_profile) */
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events; /* pairs */
+    size_t prof_next = 0, prof_used = 0;
+    double prof_sum_ms = 0.0;
+    long long prof_count = 0;
 
     void release() {
         cudaFree(params_dev); cudaFree(theta_dev); cudaFree(partials); cudaFree(result_dev);
@@ -356,6 +362,23 @@ int prepare(ad4cl_kernel* k, int nparams) {
     return AD4CL_OK;
 }
 
+/* fold the recorded event pairs into the running mean (synchronises the stream) */
+int drain_profile(ad4cl_kernel* k) {
+    if (k->prof_used == 0) return AD4CL_OK;
+    CUDA_TRY(cudaStreamSynchronize(k->ctx->stream));
+    const size_t pairs = k->prof_events.size() / 2;
+    size_t idx = (k->prof_next + pairs - k->prof_used) % pairs;
+    for (size_t i = 0; i < k->prof_used; i++) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, k->prof_events[2 * idx], k->prof_events[2 * idx + 1]));
+        k->prof_sum_ms += ms;
+        k->prof_count++;
+        idx = (idx + 1) % pairs;
+    }
+    k->prof_used = 0;
+    return AD4CL_OK;
+}
+
 /* enqueue pack + fused kernel + second stage on the context's stream */
 int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue) {
     cudaStream_t st = k->ctx->stream;
@@ -400,6 +423,18 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
                 break;
         }
     }
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (k->profiling) {
+        if (k->prof_used == k->prof_events.size() / 2) {
+            int rc = drain_profile(k);
+            if (rc != AD4CL_OK) return rc;
+        }
+        pe0 = k->prof_events[2 * k->prof_next];
+        pe1 = k->prof_events[2 * k->prof_next + 1];
+        k->prof_next = (k->prof_next + 1) % (k->prof_events.size() / 2);
+        k->prof_used++;
+        CUDA_TRY(cudaEventRecord(pe0, st));
+    }
     if (k->entry) {
         CUDA_TRY(cudaLaunchKernel(k->entry, dim3(k->grid), dim3(k->block), argv.data(), k->smem, st));
     } else {
@@ -407,6 +442,7 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
                 (CUstream) st, argv.data(), nullptr);
         if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuLaunchKernel(%s) failed: %d", k->name.c_str(), (int) r);
     }
+    if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
     const int ncols = P + 3;
     const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
     ad4cl_reduce_partials<<<ncols, 256, 0, st>>>(k->partials, k->grid, ncols, P,
@@ -647,6 +683,7 @@ int ad4cl_cuda_kernel_free(ad4cl_kernel* k) {
     k->release();
     if (k->ev0) cudaEventDestroy(k->ev0);
     if (k->ev1) cudaEventDestroy(k->ev1);
+    for (auto& e : k->prof_events) cudaEventDestroy(e);
     if (k->module && driver().cuModuleUnload) driver().cuModuleUnload(k->module);
     delete k;
     return AD4CL_OK;
@@ -772,6 +809,34 @@ int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f
     if (grad) memcpy(grad, k->result_pinned, sizeof (double) * (size_t) nparams);
     k->stats.ops = k->result_pinned[nparams + 1];
     k->stats.slots = k->result_pinned[nparams + 2];
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_profile(ad4cl_kernel* k, int enable) {
+    if (!k) return fail(AD4CL_ERR_INVALID, "kernel is NULL");
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    if (enable && k->prof_events.empty()) {
+        k->prof_events.resize(2 * 64);
+        for (auto& e : k->prof_events) CUDA_TRY(cudaEventCreate(&e));
+    }
+    if (!enable) {
+        int rc = drain_profile(k);
+        if (rc != AD4CL_OK) return rc;
+    }
+    k->profiling = enable != 0;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* k, double* mean_ms, long long* launches, int reset) {
+    if (!k || !mean_ms || !launches) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    int rc = drain_profile(k);
+    if (rc != AD4CL_OK) return rc;
+    *launches = k->prof_count;
+    *mean_ms = k->prof_count ? k->prof_sum_ms / (double) k->prof_count : 0.0;
+    if (reset) {
+        k->prof_sum_ms = 0.0;
+        k->prof_count = 0;
+    }
     return AD4CL_OK;
 }
 

@@ -85,6 +85,8 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_eval_device.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int]
     lib.ad4cl_cuda_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
+    lib.ad4cl_cuda_kernel_profile.argtypes = [c_void_p, c_int]
+    lib.ad4cl_cuda_kernel_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_longlong), c_int]
     return lib
 
 
@@ -211,6 +213,16 @@ class Kernel:
         _check(lib.ad4cl_cuda_last_stats(self._h, byref(s)))
         return {"ops": s.ops, "slots": s.slots, "grid": s.grid, "block": s.block, "smem_bytes": s.smem_bytes,
                 "arena_bytes": s.arena_bytes, "kernel_ms": s.kernel_ms}
+
+    def profile(self, enable: bool = True) -> None:
+        """CUDA-event timing of the fused kernel alone (CL_PROFILING analogue)."""
+        _check(lib.ad4cl_cuda_kernel_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset: bool = True) -> tuple[float, int]:
+        """-> (mean ms per launch of the fused kernel, launches seen)."""
+        ms, n = c_double(), c_longlong()
+        _check(lib.ad4cl_cuda_kernel_profile_read(self._h, byref(ms), byref(n), 1 if reset else 0))
+        return ms.value, n.value
 
     def free(self) -> None:
         if self._h:

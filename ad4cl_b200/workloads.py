@@ -62,7 +62,7 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
         kind = name.split("_")[1]
         X, y, beta = synth.regression(n, p, kind, start, count)
         ops = (2 * p + 1) if kind == "linear" else (2 * p + 4)
-        slots = (3 * p + 1) if kind == "linear" else (3 * p + 5)
+        slots = (3 * p + 1) if kind == "linear" else (3 * p + 4)
         return Workload(name, name, beta, X, y, count, i0=p,
                         epilogue="half_n_log" if kind == "linear" else "sum", epilogue_n=n,
                         max_ops=ops, max_slots=slots, ops_total=ops * count, slots_total=slots * count,
@@ -81,8 +81,8 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
                         extra={"steps": steps})
     if name == "op_zoo":
         d0, theta = synth.op_zoo(n)
-        return Workload(name, name, theta, d0[start:start + count], None, count, max_ops=48, max_slots=64,
-                        ops_total=43 * count, slots_total=0, input_bytes=8 * count)
+        return Workload(name, name, theta, d0[start:start + count], None, count, max_ops=48, max_slots=96,
+                        ops_total=47 * count, slots_total=0, input_bytes=8 * count)
     raise KeyError(name)
 
 

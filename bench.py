@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 objective+gradient evaluations per second of the AD hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload catch_at_age] [--n 10000000]
+
+One "step" is ONE evaluation: theta in -> objective and full gradient out, i.e.
+forward record + adjoint sweep + reduction over all work-items (+ the all-reduce
+of the [gradient, sum] vector when N > 1).  Default workload = BASELINE.json
+config 4 (the configuration the metric's target is quoted on): catch-at-age
+negative log-likelihood, 10^7 observations x 100 parameters, observations sharded
+contiguously over the N GPUs (strong scaling: the evaluation is fixed, more GPUs
+split it).  Prints ONE JSON line on rank 0.
+
+  value     evals/s with theta and the result resident in HBM (device timed)
+  e2e       evals/s through the C ABI with HOST theta / HOST result: pinned
+            h2d of theta + launches + d2h of [grad, f, ops, slots] every step.
+            The observations stay device resident between evaluations, exactly as
+            in the reference protocol (test/admb/simple.cpp:283-286 re-uploads
+            only gs, a, b per evaluation; x, y are uploaded once, :206-230).
+  roofline  the fused record+sweep+reduce kernel: algorithmic bytes (SURVEY 8d:
+            24 B per operand slot + inputs + 8(P+1)) / CUDA-event time of that
+            launch, against the measured HBM copy bandwidth.
+  cpu_baseline / --impl reference
+            the reference's own ad.cl + ad4cl.h compiled for the host
+            (oracle/_ref, kind "reference"; oracle/ port otherwise) on a bounded
+            sample of the same workload, scaled per observation to the full n.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "fp64 objective+gradient evals/s (N obs)"
+UNIT = "evals/s"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.05)
+
+    def finish(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:  # noqa: BLE001
+            return local_rank
+    return local_rank
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_eval_rate(workload: str, n_full: int, budget_s: float, steps: int = 1, warmup: int = 0):
+    """Times the reference CPU implementation on a bounded sample of `workload`.
+    Returns (evals/s scaled to n_full observations, dict describing the run)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle_api as O
+    from ad4cl_b200 import workloads as W
+
+    orc = O.best(False)
+    epi = lambda w: 1 if w.epilogue == "half_n_log" else 0  # noqa: E731
+
+    def run(n_sample, threads):
+        w = W.describe(workload, n_sample)
+        t0 = time.perf_counter()
+        r = orc.eval_objective(w.kernel, w.theta, w.d0, w.d1, w.size, w.i0, w.i1, epilogue=epi(w),
+                               threads=threads, ops_per_item=w.max_ops)
+        return time.perf_counter() - t0, r
+
+    quantum = 400 if workload == "catch_at_age" else 1
+    probe_n = 40000 // quantum * quantum
+    ncpu = os.cpu_count() or 1
+    t1, _ = run(probe_n, 1)
+    t1, _ = run(probe_n, 1)
+    best_threads, per_obs = 1, t1 / probe_n
+    if ncpu > 1:
+        tn, _ = run(probe_n, ncpu)
+        tn, _ = run(probe_n, ncpu)
+        if tn < t1:
+            best_threads, per_obs = ncpu, tn / probe_n
+    # 40 B/entry on the reference's global stack: keep the sample inside host memory
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:  # noqa: BLE001
+        avail = 8 << 30
+    w_probe = W.describe(workload, probe_n)
+    bytes_per_obs = (w_probe.max_ops + 2) * 40 + 64
+    n_mem = int(0.4 * avail / bytes_per_obs)
+    n_time = int(budget_s / max(steps + warmup, 1) / per_obs)
+    n_sample = max(quantum, min(n_full, n_mem, n_time, 2_000_000) // quantum * quantum)
+    times = []
+    for i in range(warmup + steps):
+        t, r = run(n_sample, best_threads)
+        if i >= warmup:
+            times.append(t)
+    t_step = float(np.mean(times))
+    rate_full = 1.0 / (t_step * (n_full / n_sample))
+    info = {"value": rate_full, "unit": UNIT, "cores": best_threads, "kind": orc.kind,
+            "sample": f"{workload}: {n_sample} of {n_full} observations per step ({t_step * 1e3:.1f} ms measured, "
+                      f"record {r['t_ms'][0]:.0f} + host sum {r['t_ms'][1]:.0f} + serial sweep {r['t_ms'][2]:.0f} ms), "
+                      f"scaled linearly to {n_full}; best of 1 and {ncpu} host threads",
+            "host_cpus": ncpu, "ms_per_step_sample": t_step * 1e3, "n_sample": n_sample}
+    return rate_full, info
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="catch_at_age")
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--tape-steps", type=int, default=333, help="tape_stress: recurrence steps (3 ops each)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--acc", default="auto")
+    ap.add_argument("--tape", default="auto")
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--local-size", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n, K, Wm = args.n, args.steps, args.warmup
+    wl_kw = {"steps": args.tape_steps} if args.workload == "tape_stress" else {}
+
+    from ad4cl_b200 import workloads as W
+    full = W.describe(args.workload, 400 if args.workload == "catch_at_age" else 8, **wl_kw)
+    config = {"workload": f"{args.workload} ({'BASELINE config 4: ' if args.workload == 'catch_at_age' else ''}"
+                          f"{n} observations x {full.nparams} parameters)",
+              "n_obs": n, "n_params": full.nparams,
+              "parallelism": f"observations sharded contiguously over {args.gpus} GPU(s)"
+                             + (", one NCCL all-reduce of [grad, sum] per evaluation" if args.gpus > 1 else "")}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rate, info = cpu_eval_rate(args.workload, n, budget_s=150.0, steps=K, warmup=Wm)
+        line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": K, "warmup": Wm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": info,
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from ad4cl_b200 import host
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = host.Context(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    ctx.use_stream(stream.cuda_stream)
+
+    w = W.describe(args.workload, n, rank=rank, world=world, **wl_kw)
+    P = w.nparams
+    cfg = {}
+    if args.acc != "auto":
+        cfg["acc"] = args.acc
+    if args.tape != "auto":
+        cfg["tape"] = args.tape
+    if args.window:
+        cfg["window"] = args.window
+    if args.local_size:
+        cfg["local_size"] = args.local_size
+    if args.blocks_per_sm:
+        cfg["blocks_per_sm"] = args.blocks_per_sm
+    k = W.bind(ctx, w, **cfg)
+
+    theta_host = torch.from_numpy(np.ascontiguousarray(w.theta)).pin_memory()
+    result_host = torch.empty(P + 3, dtype=torch.float64).pin_memory()
+    theta_dev = theta_host.to(dev)
+    result_dev = torch.zeros(P + 3, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    epilogue_local = world == 1
+
+    def step_device():
+        k.eval_device(theta_dev.data_ptr(), P, result_dev.data_ptr(), want_grad=True, apply_epilogue=epilogue_local)
+        if world > 1:
+            dist.all_reduce(result_dev)        # [grad..., S, ops, slots] summed over shards (sum epilogue only)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(Wm):
+        step_device()
+    torch.cuda.synchronize(dev)
+    k.check()
+    st_result = result_dev.cpu().numpy()
+
+    # ---- value: K device-timed steps, L2 flushed (untimed) before each
+    k.profile(True)
+    k.profile_read(reset=True)
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    sampler.start()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        starts[i].record(stream)
+        step_device()
+        ends[i].record(stream)
+    barrier()
+    clocks = sampler.finish()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    kernel_ms, kernel_launches = k.profile_read(reset=True)
+    k.profile(False)
+    k.check()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = K / (total_ms * 1e-3)
+
+    # ---- e2e: host theta -> host result every step (wall clock around the API call)
+    e2e_times = []
+    for i in range(Wm + K):
+        flush.fill_(i & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            f_host, g_host = k.eval(w.theta)
+        else:
+            theta_dev.copy_(theta_host, non_blocking=True)
+            step_device()
+            result_host.copy_(result_dev, non_blocking=True)
+            stream.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= Wm:
+            e2e_times.append(dt)
+    te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = K / float(te.item())
+
+    # ---- roofline of the dominant kernel (this rank's shard; rank 0 reports)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    alg_bytes = w.algorithmic_bytes()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(REPO, "profiles", "dram_traffic.json")))
+        key = f"{args.workload}:{n}:{world}"
+        traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    stats = k.stats()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": f"{w.kernel}__entry (fused record+sweep+block reduce)",
+                "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_launches,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "note": "algorithmic bytes = 24 B x operand slots + inputs + 8(P+1) (SURVEY 8d); the arena of "
+                        "resident warps can stay L2 resident for short tapes, so frac may exceed 1 (see traffic)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(config, ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
+                           l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
+                           block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
+                           tape_tier=args.tape, acc_mode=args.acc),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * (P + 3) + 4,
+                    "note": "observations device-resident across evaluations as in simple.cpp:206-230; "
+                            "theta up / [grad,f,ops,slots]+status down every step"},
+            "gpu_launches": 3 * K, "clocks": clocks, "roofline": roofline,
+            "ad_ops_per_s": float(st_result[P + 1]) * value,
+            "objective": float(st_result[P])}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, info = cpu_eval_rate(args.workload, n, budget_s=25.0)
+        line["cpu_baseline"] = info
+    k.free()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -169,6 +169,14 @@ int ad4cl_cuda_eval_device(ad4cl_kernel* kernel, const double* theta_dev, int np
 /* synchronise the stream and report tape overflow / window errors of queued evaluations */
 int ad4cl_cuda_check(ad4cl_kernel* kernel);
 int ad4cl_cuda_last_stats(ad4cl_kernel* kernel, ad4cl_eval_stats* stats);
+/*
+ * Opt-in device timing of the fused record+sweep+reduce kernel ALONE (CUDA events
+ * recorded on the launching stream around that one launch; the analogue of the
+ * reference's CL_PROFILING event.getProfilingInfo, test/admb/simple.cpp:301-310).
+ * _read synchronises the stream and returns the mean over the launches seen.
+ */
+int ad4cl_cuda_kernel_profile(ad4cl_kernel* kernel, int enable);
+int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* kernel, double* mean_ms, long long* launches, int reset);
 
 #ifdef __cplusplus
 }

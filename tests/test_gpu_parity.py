@@ -81,7 +81,7 @@ def test_far_operands(ctx, oracle_api, window, far):
     ring those operands go through the far-adjoint plane."""
     w = W.describe("catch_at_age", 4000)
     ref, _ = oracle_eval(oracle_api, w, False)
-    k = W.bind(ctx, w, window=window, far_plane=far)
+    k = W.bind(ctx, w, window=window, far_plane=far, local_size=64 if window > 64 else None)
     try:
         f, g = k.eval(w.theta)
         f2, g2 = k.eval(w.theta)   # the arena (far bitmap) must be left clean
