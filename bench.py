@@ -211,7 +211,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = host.Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # one non-default stream carries everything: our launches, NCCL, the L2 flush and the timing events
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ctx.use_stream(stream.cuda_stream)
 
     w = W.describe(args.workload, n, rank=rank, world=world, **wl_kw)
