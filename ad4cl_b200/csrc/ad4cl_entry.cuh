@@ -137,11 +137,11 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     tape_bind(tape, region, L.cap_slots, L.cap_ops, P, L.window, L.use_far != 0);
 
     SweepTarget T;
-    T.ring = ring + tid;
-    T.stride = B;
+    T.ring = smem_u32(ring + tid);
+    T.stride = (unsigned) B * 8u;
     T.mode = L.acc_mode;
-    T.thread_acc = thread_acc + tid;
-    T.warp_acc = warp_acc + (size_t) warp * P;
+    T.thread_acc = smem_u32(thread_acc + tid);
+    T.warp_acc = smem_u32(warp_acc + (size_t) warp * P);
     T.global_acc = L.global_grad;
 
     double sum = 0.0;

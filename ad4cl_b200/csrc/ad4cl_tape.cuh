@@ -165,18 +165,35 @@ enum AccMode : int {
     kAccGlobal = 2, /* fp64 RED into a global gradient array (many independents) */
 };
 
+/* shared-memory accesses by 32-bit shared-window address: no generic-pointer
+   conversion in the sweep's inner loop */
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" : : "r"(addr), "d"(v) : "memory");
+}
+
 struct SweepTarget {
-    double* ring;        /* this thread's ring column: entry r at ring[r * stride] */
-    int stride;          /* block size */
+    unsigned ring;        /* shared address of this thread's ring column; entry r at ring + r * stride */
+    unsigned stride;      /* bytes between consecutive entries of a column (block size * 8) */
     int mode;
-    double* thread_acc;  /* kAccThread: this thread's column, parameter p at thread_acc[p * stride] */
-    double* warp_acc;    /* kAccWarp: this warp's row of P accumulators */
-    double* global_acc;  /* kAccGlobal: gradient array indexed by id */
+    unsigned thread_acc;  /* kAccThread: shared address of this thread's column, parameter p at + p * stride */
+    unsigned warp_acc;    /* kAccWarp: shared address of this warp's row of P accumulators */
+    double* global_acc;   /* kAccGlobal: gradient array indexed by id */
 };
 
 __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param, int id, double c) {
     if (T.mode == kAccThread) {
-        if (is_param) T.thread_acc[(size_t) id * T.stride] += c;
+        if (is_param) {
+            const unsigned a = T.thread_acc + (unsigned) id * T.stride;
+            sts_f64(a, lds_f64(a) + c);
+        }
     } else if (T.mode == kAccWarp) {
         /* all 32 lanes arrive here together; group lanes by parameter id in
            lowest-lane-first order so the summation order is fixed */
@@ -187,13 +204,18 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
             const bool mine = is_param && id == lid;
             const unsigned members = __ballot_sync(0xffffffffu, mine);
             const double v = warp_sum(mine ? c : 0.0);
-            if ((threadIdx.x & 31) == 0) T.warp_acc[lid] += v;
+            if ((threadIdx.x & 31) == 0) {
+                const unsigned a = T.warp_acc + (unsigned) lid * 8u;
+                sts_f64(a, lds_f64(a) + v);
+            }
             pending &= ~members;
         }
     } else {
         if (is_param) atomicAdd(&T.global_acc[id], c);
     }
 }
+
+constexpr int kSweepUnroll = 4; /* slots fetched per batch; two batches are in flight */
 
 /*
  * Reverse sweep of the current work-item's tape, seeded with 1 at `out_id`.
@@ -202,60 +224,96 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
  * popped from the ring when its END slot is met, and each slot scatters w * dx
  * to the ring (recent temporaries), the far plane (old temporaries) or the
  * accumulator (independents).  All lanes of the warp iterate together (tapes
- * of neighbouring work-items normally have identical shape).
+ * of neighbouring work-items normally have identical shape).  The stream is
+ * read kSweepUnroll rows at a time, one batch ahead of the batch being
+ * processed, so the L2/HBM latency of a row is overlapped with the adjoint
+ * arithmetic of the previous ones.
  */
 __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T) {
+    constexpr int U = kSweepUnroll;
     const int first_temp = t.first_temp;
-    const int wmask = t.window - 1;
+    const int window = t.window;
+    const int wmask = window - 1;
+    const int id_off = t.id_off;
+    const bool far = t.far_adj != nullptr;
     int p = t.nops;
     unsigned s = t.kept;
-    char* cur = t.cur;
+    const char* cur = t.cur;
     const int seed_pos = out_id - first_temp;
     sweep_param(T, out_id >= 0 && out_id < first_temp, out_id, 1.0);
 
     double w = 0.0;
     unsigned bits = 0;
     int bits_word = -1;
+
+    double dx_now[U], dx_next[U];
+    int id_now[U], id_next[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        if (s > (unsigned) j) {
+            const char* row = cur - (j + 1) * kRowBytes;
+            dx_now[j] = *reinterpret_cast<const double*> (row);
+            id_now[j] = *reinterpret_cast<const int*> (row + id_off);
+        } else {
+            dx_now[j] = 0.0;
+            id_now[j] = kNopFlag;
+        }
+    }
     while (__any_sync(0xffffffffu, s > 0)) {
-        const bool act = s > 0;
-        double dx = 0.0;
-        int idw = kNopFlag;
-        if (act) {
-            cur -= kRowBytes;
-            dx = *reinterpret_cast<const double*> (cur);
-            idw = *reinterpret_cast<const int*> (cur + t.id_off);
-            --s;
+        const unsigned s_after = s > (unsigned) U ? s - U : 0u;
+        cur -= U * kRowBytes;
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            if (s_after > (unsigned) j) {
+                const char* row = cur - (j + 1) * kRowBytes;
+                dx_next[j] = *reinterpret_cast<const double*> (row);
+                id_next[j] = *reinterpret_cast<const int*> (row + id_off);
+            } else {
+                dx_next[j] = 0.0;
+                id_next[j] = kNopFlag;
+            }
         }
-        if (idw & kEndFlag) {
-            --p;
-            double* r = T.ring + (size_t) (p & wmask) * T.stride;
-            w = *r;
-            *r = 0.0;
-            if (p == seed_pos) w += 1.0;
-            if (t.far_adj != nullptr) {
-                const int word = p >> 5;
-                if (word != bits_word) {
-                    if (bits_word >= 0 && bits != 0)
-                        *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
-                    bits_word = word;
-                    bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) word * kBitsRowBytes);
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int idw = id_now[j];
+            if (idw < 0) { /* END: this slot opens the next (older) operator */
+                --p;
+                const unsigned r = T.ring + (unsigned) (p & wmask) * T.stride;
+                w = lds_f64(r);
+                sts_f64(r, 0.0);
+                if (p == seed_pos) w += 1.0;
+                if (far) {
+                    const int word = p >> 5;
+                    if (word != bits_word) {
+                        if (bits_word >= 0 && bits != 0)
+                            *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
+                        bits_word = word;
+                        bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) word * kBitsRowBytes);
+                    }
+                    if ((bits >> (p & 31)) & 1u)
+                        w += *reinterpret_cast<const double*> (t.far_adj + (size_t) p * kFarRowBytes);
                 }
-                if ((bits >> (p & 31)) & 1u)
-                    w += *reinterpret_cast<const double*> (t.far_adj + (size_t) p * kFarRowBytes);
             }
-        }
-        const int id = idw & kIdMask;
-        const double c = w * dx;
-        const bool live = act && !(idw & kNopFlag);
-        if (live && id >= first_temp) {
-            const int pos = id - first_temp;
-            if (p - pos < t.window) {
-                T.ring[(size_t) (pos & wmask) * T.stride] += c;
-            } else if (t.far_adj != nullptr) {
-                *reinterpret_cast<double*> (t.far_adj + (size_t) pos * kFarRowBytes) += c;
+            const int id = idw & kIdMask;
+            const double c = w * dx_now[j];
+            const bool live = !(idw & kNopFlag);
+            if (live && id >= first_temp) {
+                const int pos = id - first_temp;
+                if (p - pos < window) {
+                    const unsigned a = T.ring + (unsigned) (pos & wmask) * T.stride;
+                    sts_f64(a, lds_f64(a) + c);
+                } else if (far) {
+                    *reinterpret_cast<double*> (t.far_adj + (size_t) pos * kFarRowBytes) += c;
+                }
             }
+            sweep_param(T, live && id < first_temp, id, c);
         }
-        sweep_param(T, live && id < first_temp, id, c);
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            dx_now[j] = dx_next[j];
+            id_now[j] = id_next[j];
+        }
+        s = s_after;
     }
     if (bits_word >= 0 && bits != 0)
         *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
