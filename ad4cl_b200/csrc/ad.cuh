@@ -128,7 +128,7 @@ AD4CL_DEV void ad_init_var_g(struct ad_gradient_structure* gs, struct ad_variabl
     var->value = value;
     if (gs->recording == 1) {
         ad4cl::tape_push(gs->tape, 0.0, 0, ad4cl::kEndFlag | ad4cl::kNopFlag);
-        var->id = ad4cl::tape_close_op(gs->tape);
+        var->id = ad4cl::tape_close_op(gs->tape, 1);
         gs->counter = gs->tape->nops;
     } else {
         var->id = 0;
@@ -141,7 +141,7 @@ namespace ad4cl {
 
 AD4CL_DEV int record1(struct ad_gradient_structure* gs, double dx, int id) {
     tape_push(gs->tape, dx, id, kEndFlag);
-    const int r = tape_close_op(gs->tape);
+    const int r = tape_close_op(gs->tape, 1);
     gs->counter = gs->tape->nops;
     return r;
 }
@@ -149,7 +149,7 @@ AD4CL_DEV int record1(struct ad_gradient_structure* gs, double dx, int id) {
 AD4CL_DEV int record2(struct ad_gradient_structure* gs, double dx0, int id0, double dx1, int id1) {
     tape_push(gs->tape, dx0, id0, 0);
     tape_push(gs->tape, dx1, id1, kEndFlag);
-    const int r = tape_close_op(gs->tape);
+    const int r = tape_close_op(gs->tape, 2);
     gs->counter = gs->tape->nops;
     return r;
 }

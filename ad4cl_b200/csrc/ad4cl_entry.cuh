@@ -36,8 +36,7 @@ struct LaunchInfo {
     int window;             /* adjoint ring entries per thread (power of two) */
     int use_far;            /* far-adjoint plane present in the arena */
     int tape_in_smem;       /* 1: tape rows live in dynamic shared memory */
-    unsigned cap_slots;     /* per-thread tape capacity */
-    int cap_ops;
+    unsigned cap_slots;     /* per-thread tape capacity (operand slots) */
     char* arena;            /* HBM arena: one warp region per resident warp */
     unsigned long long warp_region;  /* bytes per warp region */
     double* partials;       /* [gridDim.x][ncols], ncols = nparams + 3 */
@@ -83,7 +82,7 @@ extern __shared__ __align__(16) unsigned char ad4cl_dyn_smem[];
  *   tape rows [NW][smem_region]     tape_in_smem only (bytes)
  */
 __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int window, int acc_mode,
-        bool tape_in_smem, unsigned cap_slots, int cap_ops, bool far) {
+        bool tape_in_smem, unsigned cap_slots, bool far) {
     const int nw = block / 32;
     size_t d = (size_t) window * block;
     if (acc_mode == kAccThread) d += (size_t) nparams * block;
@@ -91,7 +90,7 @@ __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int w
     d += (size_t) nw * (nparams + 3);
     size_t bytes = d * sizeof (double);
     bytes = (bytes + 127) & ~(size_t) 127;
-    if (tape_in_smem) bytes += (size_t) nw * warp_region_bytes(cap_slots, cap_ops, far);
+    if (tape_in_smem) bytes += (size_t) nw * warp_region_bytes(cap_slots, far);
     return bytes;
 }
 
@@ -124,9 +123,9 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     if (L.tape_in_smem) {
         region = reinterpret_cast<char*> (ad4cl_dyn_smem) + dbl_bytes + (size_t) warp * L.warp_region;
         if (L.use_far) { /* the far bitmap must start clear */
-            unsigned* bits = reinterpret_cast<unsigned*> (region + (size_t) L.cap_slots * kRowBytes
-                    + (size_t) L.cap_ops * kFarRowBytes);
-            for (int i = lane; i < ((L.cap_ops + 31) / 32) * 32; i += 32) bits[i] = 0u;
+            unsigned* bits = reinterpret_cast<unsigned*> (region + (size_t) (L.cap_slots + kGuardRows) * kRowBytes
+                    + (size_t) L.cap_slots * kFarRowBytes);
+            for (int i = lane; i < (int) ((L.cap_slots + 31) / 32) * 32; i += 32) bits[i] = 0u;
         }
     } else {
         region = L.arena + ((size_t) blockIdx.x * nw + warp) * L.warp_region;
@@ -134,7 +133,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     __syncthreads();
 
     ThreadTape tape;
-    tape_bind(tape, region, L.cap_slots, L.cap_ops, P, L.window, L.use_far != 0);
+    tape_bind(tape, region, L.cap_slots, P, L.window, L.use_far != 0);
 
     SweepTarget T;
     T.ring = smem_u32(ring + tid);
@@ -190,7 +189,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     {
         const double s = warp_sum(sum);
         const double o = warp_sum((double) tape.total_ops);
-        const double k = warp_sum((double) tape.total_slots);
+        const double k = warp_sum((double) (tape.total_slot_bytes / kRowBytes));
         if (lane == 0) {
             red[(size_t) warp * ncols + P] = s;
             red[(size_t) warp * ncols + P + 1] = o;
@@ -217,6 +216,9 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
  * from the entry's own parameters.
  */
 #define AD4CL_UNPAREN(...) __VA_ARGS__
+#ifndef AD4CL_MIN_BLOCKS
+#define AD4CL_MIN_BLOCKS 4 /* 4 x 256 threads per SM: caps the entry at 64 registers */
+#endif
 #ifndef AD4CL_ENTRY_SUFFIX
 #define AD4CL_ENTRY_SUFFIX /* the two ahead-of-time builds of one kernel need distinct symbols */
 #endif
@@ -224,7 +226,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 #define AD4CL_CAT3(a, b, c) AD4CL_CAT3_(a, b, c)
 #define AD4CL_ENTRY_NAME(NAME) AD4CL_CAT3(NAME, __entry, AD4CL_ENTRY_SUFFIX)
 #define AD4CL_OBJECTIVE_ENTRY(NAME, PARAMS, ARGS)                                         \
-    extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK)                          \
+    extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK, AD4CL_MIN_BLOCKS)        \
     AD4CL_ENTRY_NAME(NAME)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {              \
         ad4cl::run_objective(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out) { \
             struct ad_entry* gradient_stack = nullptr;                                     \

@@ -53,100 +53,99 @@ enum Status : int {
 
 struct ThreadTape {
     char* cur;            /* address of this lane's partial in the next free row */
+    char* begin;          /* row 0 */
+    char* end;            /* begin + capacity; two guard rows follow (an operator has <= 2 slots) */
     int id_off;           /* byte offset from a row's partial to its id word, this lane */
-    unsigned nslots;      /* slots pushed by the current work-item */
-    unsigned kept;        /* of which actually stored (== nslots unless the tape overflowed) */
-    unsigned cap_slots;
     int nops;             /* operators recorded by the current work-item */
-    int cap_ops;
     int first_temp;       /* number of independents: ids >= first_temp are tape positions */
+    int far_lim;          /* operand ids in [first_temp, far_lim] are `window` or more operators old */
     int window;           /* W, a power of two */
     char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
     char* far_bits;       /* this lane's far bitmap column (row stride kBitsRowBytes) */
     int status;           /* sticky Status bits */
     long long total_ops;  /* statistics over all work-items of this thread */
-    long long total_slots;
+    long long total_slot_bytes;
 };
 
-/* Bytes one warp needs in the arena for cap_slots slots and cap_ops operators. */
-__host__ __device__ inline size_t warp_region_bytes(unsigned cap_slots, int cap_ops, bool far) {
-    size_t b = (size_t) cap_slots * kRowBytes;
+constexpr int kGuardRows = 2;
+
+/* Bytes one warp needs in the arena for cap_slots slots (far planes are sized
+   by slots too: an operator has at least one slot). */
+__host__ __device__ inline size_t warp_region_bytes(unsigned cap_slots, bool far) {
+    size_t b = (size_t) (cap_slots + kGuardRows) * kRowBytes;
     if (far) {
-        b += (size_t) cap_ops * kFarRowBytes;
-        b += (size_t) ((cap_ops + 31) / 32) * kBitsRowBytes;
+        b += (size_t) cap_slots * kFarRowBytes;
+        b += (size_t) ((cap_slots + 31) / 32) * kBitsRowBytes;
     }
     return (b + 127) & ~(size_t) 127;
 }
 
 __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsigned cap_slots,
-        int cap_ops, int first_temp, int window, bool far) {
+        int first_temp, int window, bool far) {
     const int lane = threadIdx.x & 31;
-    t.cur = warp_region + lane * 8;
+    t.begin = warp_region + lane * 8;
+    t.cur = t.begin;
+    t.end = t.begin + (size_t) cap_slots * kRowBytes;
     t.id_off = kRowIdOffset - lane * 4;
-    t.nslots = 0;
-    t.kept = 0;
-    t.cap_slots = cap_slots;
     t.nops = 0;
-    t.cap_ops = cap_ops;
     t.first_temp = first_temp;
     t.window = window;
+    t.far_lim = first_temp - window;
     if (far) {
-        char* fa = warp_region + (size_t) cap_slots * kRowBytes;
+        char* fa = warp_region + (size_t) (cap_slots + kGuardRows) * kRowBytes;
         t.far_adj = fa + lane * 8;
-        t.far_bits = fa + (size_t) cap_ops * kFarRowBytes + lane * 4;
+        t.far_bits = fa + (size_t) cap_slots * kFarRowBytes + lane * 4;
     } else {
         t.far_adj = nullptr;
         t.far_bits = nullptr;
     }
     t.status = kOk;
     t.total_ops = 0;
-    t.total_slots = 0;
+    t.total_slot_bytes = 0;
 }
 
-/* An operand that is `window` or more operators old cannot use the ring. */
-__device__ __forceinline__ void tape_note_far(ThreadTape* t, int pos) {
-    if (t->far_adj == nullptr) {
-        t->status |= kErrWindow;
-        return;
-    }
-    unsigned* word = reinterpret_cast<unsigned*> (t->far_bits + (size_t) (pos >> 5) * kBitsRowBytes);
+/* An operand that is `window` or more operators old cannot use the ring: flag
+   it in the bitmap and clear its far adjoint on first use.  Cold path. */
+static __device__ __noinline__ int tape_note_far(char* far_adj, char* far_bits, int pos) {
+    if (far_adj == nullptr) return kErrWindow;
+    unsigned* word = reinterpret_cast<unsigned*> (far_bits + (size_t) (pos >> 5) * kBitsRowBytes);
     const unsigned bit = 1u << (pos & 31);
     const unsigned old = *word;
     if (!(old & bit)) {
         *word = old | bit;
-        *reinterpret_cast<double*> (t->far_adj + (size_t) pos * kFarRowBytes) = 0.0;
+        *reinterpret_cast<double*> (far_adj + (size_t) pos * kFarRowBytes) = 0.0;
     }
+    return kOk;
 }
 
-/* Push one (partial, operand) slot.  `flags` is 0, kEndFlag or kEndFlag|kNopFlag. */
+/* Push one (partial, operand) slot.  `flags` is 0, kEndFlag or kEndFlag|kNopFlag.
+   The store is unconditional (guard rows absorb the last operator of an
+   overflowing tape); capacity is checked once per operator in tape_close_op. */
 __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
-    if (t->nslots < t->cap_slots && t->nops < t->cap_ops) {
-        if (id >= t->first_temp && !(flags & kNopFlag)) {
-            const int pos = id - t->first_temp;
-            if (t->nops - pos >= t->window) tape_note_far(t, pos);
-        }
-        *reinterpret_cast<double*> (t->cur) = dx;
-        *reinterpret_cast<int*> (t->cur + t->id_off) = id | flags;
-        t->cur += kRowBytes;
-        t->kept++;
-    } else {
-        t->status |= kErrTapeOverflow;
-    }
-    t->nslots++;
+    if (id >= t->first_temp && id <= t->far_lim)
+        t->status |= tape_note_far(t->far_adj, t->far_bits, id - t->first_temp);
+    *reinterpret_cast<double*> (t->cur) = dx;
+    *reinterpret_cast<int*> (t->cur + t->id_off) = id | flags;
+    t->cur += kRowBytes;
 }
 
-/* Close the operator whose slots were just pushed; returns its result id. */
-__device__ __forceinline__ int tape_close_op(ThreadTape* t) {
+/* Close the operator whose `k` slots were just pushed; returns its result id. */
+__device__ __forceinline__ int tape_close_op(ThreadTape* t, int k) {
+    if (t->cur > t->end) { /* does not fit: drop the operator, keep the pointer inside the guard */
+        t->status |= kErrTapeOverflow;
+        t->cur -= k * kRowBytes;
+        return t->first_temp + t->nops;
+    }
+    t->far_lim++;
     return t->first_temp + t->nops++;
 }
 
 /* Forget the current work-item's tape (the arena column is reused). */
 __device__ __forceinline__ void tape_rewind(ThreadTape& t) {
     t.total_ops += t.nops;
-    t.total_slots += t.nslots;
-    t.cur -= (size_t) t.kept * kRowBytes;
-    t.nslots = 0;
-    t.kept = 0;
+    t.total_slot_bytes += t.cur - t.begin;
+    t.cur = t.begin;
+    t.far_lim -= t.nops;
     t.nops = 0;
 }
 
@@ -237,7 +236,7 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
     const int id_off = t.id_off;
     const bool far = t.far_adj != nullptr;
     int p = t.nops;
-    unsigned s = t.kept;
+    unsigned s = (unsigned) (t.cur - t.begin); /* bytes of rows still to read */
     const char* cur = t.cur;
     const int seed_pos = out_id - first_temp;
     sweep_param(T, out_id >= 0 && out_id < first_temp, out_id, 1.0);
@@ -250,7 +249,7 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
     int id_now[U], id_next[U];
 #pragma unroll
     for (int j = 0; j < U; j++) {
-        if (s > (unsigned) j) {
+        if (s > (unsigned) (j * kRowBytes)) {
             const char* row = cur - (j + 1) * kRowBytes;
             dx_now[j] = *reinterpret_cast<const double*> (row);
             id_now[j] = *reinterpret_cast<const int*> (row + id_off);
@@ -260,11 +259,11 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
         }
     }
     while (__any_sync(0xffffffffu, s > 0)) {
-        const unsigned s_after = s > (unsigned) U ? s - U : 0u;
+        const unsigned s_after = s > (unsigned) (U * kRowBytes) ? s - U * kRowBytes : 0u;
         cur -= U * kRowBytes;
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            if (s_after > (unsigned) j) {
+            if (s_after > (unsigned) (j * kRowBytes)) {
                 const char* row = cur - (j + 1) * kRowBytes;
                 dx_next[j] = *reinterpret_cast<const double*> (row);
                 id_next[j] = *reinterpret_cast<const int*> (row + id_off);

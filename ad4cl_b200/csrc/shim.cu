@@ -284,14 +284,13 @@ int prepare(ad4cl_kernel* k, int nparams) {
     if (acc == AD4CL_ACC_AUTO) acc = nparams <= 16 ? AD4CL_ACC_THREAD : (nparams <= 4096 ? AD4CL_ACC_WARP : AD4CL_ACC_GLOBAL);
     const int max_ops = std::max(c.max_ops, 1);
     const unsigned cap_slots = (unsigned) (c.max_slots > 0 ? c.max_slots : 2 * max_ops);
-    const int cap_ops = max_ops + 1;
     const bool far = c.far_plane != 0;
-    int window = c.window > 0 ? pow2_at_least(c.window) : (far ? 16 : pow2_at_least(cap_ops));
+    int window = c.window > 0 ? pow2_at_least(c.window) : (far ? 16 : pow2_at_least(max_ops + 1));
     int tier = c.tape_tier;
     if (tier == AD4CL_TAPE_AUTO) tier = AD4CL_TAPE_HBM;
 
     const size_t smem = ad4cl::entry_smem_bytes(block, nparams, window, acc, tier == AD4CL_TAPE_SHARED,
-            cap_slots, cap_ops, far);
+            cap_slots, far);
     if (smem > k->ctx->prop.sharedMemPerBlockOptin)
         return fail(AD4CL_ERR_INVALID, "kernel %s needs %zu B of shared memory per block (limit %zu): "
                 "lower window/local size or use AD4CL_ACC_WARP", k->name.c_str(), smem,
@@ -305,7 +304,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     int grid = (int) std::min<long long>((long long) k->ctx->prop.multiProcessorCount * per_sm, ngroups);
     grid = std::max(grid, 1);
 
-    const size_t region = ad4cl::warp_region_bytes(cap_slots, cap_ops, far);
+    const size_t region = ad4cl::warp_region_bytes(cap_slots, far);
     const size_t arena_bytes = tier == AD4CL_TAPE_SHARED ? 0 : (size_t) grid * (block / 32) * region;
     const int ncols = nparams + 3;
 
@@ -342,7 +341,6 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.use_far = far ? 1 : 0;
     L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
     L.cap_slots = cap_slots;
-    L.cap_ops = cap_ops;
     L.arena = k->arena;
     L.warp_region = region;
     L.partials = k->partials;
