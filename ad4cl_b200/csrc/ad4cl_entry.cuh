@@ -138,7 +138,6 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     SweepTarget T;
     T.ring = smem_u32(ring + tid);
     T.stride = (unsigned) B * 8u;
-    T.mode = L.acc_mode;
     T.thread_acc = smem_u32(thread_acc + tid);
     T.warp_acc = smem_u32(warp_acc + (size_t) warp * P);
     T.global_acc = L.global_grad;
@@ -169,7 +168,11 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         body(&gs, &outv - item);
         sum += outv.value;
         /* a thread whose tape overflowed skips the sweep (the host reports the error) */
-        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) tape_sweep(tape, outv.id, T);
+        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
+            if (L.acc_mode == kAccWarp) tape_sweep<kAccWarp>(tape, outv.id, T);
+            else if (L.acc_mode == kAccThread) tape_sweep<kAccThread>(tape, outv.id, T);
+            else tape_sweep<kAccGlobal>(tape, outv.id, T);
+        }
         tape_rewind(tape);
     }
 

@@ -35,9 +35,13 @@
 
 namespace ad4cl {
 
+/* id word of a slot: [31] END  [30] NOP  [29] PARAM  [28] FAR  [27:0] payload.
+   payload = id of an independent (PARAM) or tape POSITION of a temporary. */
 constexpr int kEndFlag = (int) 0x80000000u; /* last slot of an operator */
 constexpr int kNopFlag = 0x40000000;        /* slot carries no partial (leaf variable) */
-constexpr int kIdMask = 0x3FFFFFFF;
+constexpr int kParamFlag = 0x20000000;      /* operand is an independent */
+constexpr int kFarFlag = 0x10000000;        /* operand is a temporary `window` or more operators old */
+constexpr int kIdMask = 0x0FFFFFFF;
 constexpr int kNoId = -1;                   /* "no output written" */
 
 constexpr int kRowBytes = 384;              /* 32 lanes x (8 B partial + 4 B id word) */
@@ -119,13 +123,24 @@ static __device__ __noinline__ int tape_note_far(char* far_adj, char* far_bits, 
 }
 
 /* Push one (partial, operand) slot.  `flags` is 0, kEndFlag or kEndFlag|kNopFlag.
-   The store is unconditional (guard rows absorb the last operator of an
-   overflowing tape); capacity is checked once per operator in tape_close_op. */
+   The operand is classified here (independent / recent temporary / far
+   temporary) so the sweep only tests flag bits.  The store is unconditional
+   (guard rows absorb the last operator of an overflowing tape); capacity is
+   checked once per operator in tape_close_op. */
 __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
-    if (id >= t->first_temp && id <= t->far_lim)
-        t->status |= tape_note_far(t->far_adj, t->far_bits, id - t->first_temp);
+    int word;
+    if (id < t->first_temp) {
+        word = id | kParamFlag | flags;
+    } else {
+        const int pos = id - t->first_temp;
+        word = pos | flags;
+        if (id <= t->far_lim && !(flags & kNopFlag)) {
+            t->status |= tape_note_far(t->far_adj, t->far_bits, pos);
+            word |= kFarFlag;
+        }
+    }
     *reinterpret_cast<double*> (t->cur) = dx;
-    *reinterpret_cast<int*> (t->cur + t->id_off) = id | flags;
+    *reinterpret_cast<int*> (t->cur + t->id_off) = word;
     t->cur += kRowBytes;
 }
 
@@ -181,19 +196,19 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
 struct SweepTarget {
     unsigned ring;        /* shared address of this thread's ring column; entry r at ring + r * stride */
     unsigned stride;      /* bytes between consecutive entries of a column (block size * 8) */
-    int mode;
     unsigned thread_acc;  /* kAccThread: shared address of this thread's column, parameter p at + p * stride */
     unsigned warp_acc;    /* kAccWarp: shared address of this warp's row of P accumulators */
     double* global_acc;   /* kAccGlobal: gradient array indexed by id */
 };
 
+template <int MODE>
 __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param, int id, double c) {
-    if (T.mode == kAccThread) {
+    if (MODE == kAccThread) {
         if (is_param) {
             const unsigned a = T.thread_acc + (unsigned) id * T.stride;
             sts_f64(a, lds_f64(a) + c);
         }
-    } else if (T.mode == kAccWarp) {
+    } else if (MODE == kAccWarp) {
         /* all 32 lanes arrive here together; group lanes by parameter id in
            lowest-lane-first order so the summation order is fixed */
         unsigned pending = __ballot_sync(0xffffffffu, is_param);
@@ -214,7 +229,7 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
     }
 }
 
-constexpr int kSweepUnroll = 4; /* slots fetched per batch; two batches are in flight */
+constexpr int kSweepUnroll = 4; /* rows fetched per batch; two batches are in flight */
 
 /*
  * Reverse sweep of the current work-item's tape, seeded with 1 at `out_id`.
@@ -228,28 +243,41 @@ constexpr int kSweepUnroll = 4; /* slots fetched per batch; two batches are in f
  * processed, so the L2/HBM latency of a row is overlapped with the adjoint
  * arithmetic of the previous ones.
  */
+template <int MODE>
 __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T) {
     constexpr int U = kSweepUnroll;
-    const int first_temp = t.first_temp;
-    const int window = t.window;
-    const int wmask = window - 1;
+    const int wmask = t.window - 1;
     const int id_off = t.id_off;
     const bool far = t.far_adj != nullptr;
     int p = t.nops;
-    unsigned s = (unsigned) (t.cur - t.begin); /* bytes of rows still to read */
     const char* cur = t.cur;
-    const int seed_pos = out_id - first_temp;
-    sweep_param(T, out_id >= 0 && out_id < first_temp, out_id, 1.0);
+    unsigned rows = (unsigned) ((size_t) (t.cur - t.begin) / kRowBytes);
+
+    /* seed d(out) = 1 */
+    const int seed_pos = out_id - t.first_temp;
+    sweep_param<MODE>(T, out_id >= 0 && out_id < t.first_temp, out_id, 1.0);
+    if (seed_pos >= 0 && seed_pos < p) {
+        /* operators recorded after `out` are dead; drop them when they could alias the seed's ring entry */
+        while (p - seed_pos > t.window) {
+            cur -= kRowBytes;
+            --rows;
+            if (*reinterpret_cast<const int*> (cur + id_off) < 0) --p;
+        }
+        sts_f64(T.ring + (unsigned) (seed_pos & wmask) * T.stride, 1.0);
+    }
 
     double w = 0.0;
     unsigned bits = 0;
-    int bits_word = -1;
+    if (far && p > 0) bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) ((p - 1) >> 5) * kBitsRowBytes);
+    bool bits_dirty = false;
 
+    /* the first batch takes the rows that do not fill a whole batch */
     double dx_now[U], dx_next[U];
     int id_now[U], id_next[U];
+    const unsigned head = rows & (U - 1);
 #pragma unroll
     for (int j = 0; j < U; j++) {
-        if (s > (unsigned) (j * kRowBytes)) {
+        if ((unsigned) j < head) {
             const char* row = cur - (j + 1) * kRowBytes;
             dx_now[j] = *reinterpret_cast<const double*> (row);
             id_now[j] = *reinterpret_cast<const int*> (row + id_off);
@@ -258,16 +286,23 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
             id_now[j] = kNopFlag;
         }
     }
-    while (__any_sync(0xffffffffu, s > 0)) {
-        const unsigned s_after = s > (unsigned) (U * kRowBytes) ? s - U * kRowBytes : 0u;
-        cur -= U * kRowBytes;
+    cur -= (size_t) head * kRowBytes;
+    unsigned batches = rows / U; /* whole batches still in memory */
+    bool more = true;
+    while (__any_sync(0xffffffffu, more)) {
+        const bool fetch = batches > 0;
+        if (fetch) {
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            if (s_after > (unsigned) (j * kRowBytes)) {
+            for (int j = 0; j < U; j++) {
                 const char* row = cur - (j + 1) * kRowBytes;
                 dx_next[j] = *reinterpret_cast<const double*> (row);
                 id_next[j] = *reinterpret_cast<const int*> (row + id_off);
-            } else {
+            }
+            cur -= U * kRowBytes;
+            --batches;
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; j++) {
                 dx_next[j] = 0.0;
                 id_next[j] = kNopFlag;
             }
@@ -280,42 +315,38 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
                 const unsigned r = T.ring + (unsigned) (p & wmask) * T.stride;
                 w = lds_f64(r);
                 sts_f64(r, 0.0);
-                if (p == seed_pos) w += 1.0;
                 if (far) {
-                    const int word = p >> 5;
-                    if (word != bits_word) {
-                        if (bits_word >= 0 && bits != 0)
-                            *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
-                        bits_word = word;
-                        bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) word * kBitsRowBytes);
-                    }
-                    if ((bits >> (p & 31)) & 1u)
+                    if ((bits >> (p & 31)) & 1u) {
                         w += *reinterpret_cast<const double*> (t.far_adj + (size_t) p * kFarRowBytes);
+                        bits_dirty = true;
+                    }
+                    if ((p & 31) == 0) { /* leaving this bitmap word: clear it, fetch the next */
+                        if (bits_dirty) *reinterpret_cast<unsigned*> (t.far_bits + (size_t) (p >> 5) * kBitsRowBytes) = 0u;
+                        bits_dirty = false;
+                        if (p > 0) bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) ((p - 1) >> 5) * kBitsRowBytes);
+                    }
                 }
             }
-            const int id = idw & kIdMask;
+            const int payload = idw & kIdMask;
             const double c = w * dx_now[j];
-            const bool live = !(idw & kNopFlag);
-            if (live && id >= first_temp) {
-                const int pos = id - first_temp;
-                if (p - pos < window) {
-                    const unsigned a = T.ring + (unsigned) (pos & wmask) * T.stride;
-                    sts_f64(a, lds_f64(a) + c);
-                } else if (far) {
-                    *reinterpret_cast<double*> (t.far_adj + (size_t) pos * kFarRowBytes) += c;
-                }
+            const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
+            if (cls == 0) {
+                const unsigned a = T.ring + (unsigned) (payload & wmask) * T.stride;
+                sts_f64(a, lds_f64(a) + c);
+            } else if (cls == kFarFlag) {
+                if (far) *reinterpret_cast<double*> (t.far_adj + (size_t) payload * kFarRowBytes) += c;
             }
-            sweep_param(T, live && id < first_temp, id, c);
+            sweep_param<MODE>(T, cls == kParamFlag, payload, c);
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {
             dx_now[j] = dx_next[j];
             id_now[j] = id_next[j];
         }
-        s = s_after;
+        more = fetch;
     }
-    if (bits_word >= 0 && bits != 0)
-        *reinterpret_cast<unsigned*> (t.far_bits + (size_t) bits_word * kBitsRowBytes) = 0u;
+    if (far && bits_dirty && p > 0)
+        *reinterpret_cast<unsigned*> (t.far_bits + (size_t) ((p - 1) >> 5) * kBitsRowBytes) = 0u;
 }
 
 } // namespace ad4cl
