@@ -1,0 +1,71 @@
+"""Multi-GPU evaluation: observations are sharded contiguously over the ranks
+(one process per GPU), every rank produces the raw sums of its shard
+[d S/d theta_0..P-1, S, #ops, #slots] with the single-GPU path, ONE all-reduce
+of those P+3 doubles combines them, and the scalar epilogue f = h(S),
+grad = h'(S) dS/dtheta is applied identically on every rank.
+
+The objective of every AD4CL example has this form: f = h(sum_i out_i), with
+h = identity or (n/2) log (test/admb/simple.cpp:357-365).  Nothing else crosses
+the interconnect; there is no data-path collective.
+
+`torch.distributed` is plumbing only: NCCL on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+from .workloads import shard_range  # noqa: F401  (re-exported: the sharding rule)
+
+
+def apply_epilogue(raw: torch.Tensor, nparams: int, epilogue: str, n_total: float) -> torch.Tensor:
+    """raw = [g_0..g_{P-1}, S, ops, slots] (sums over all shards) -> same layout with
+    f in place of S and the gradient scaled.  (n/2) log S: simple.cpp:365, main.cpp:417."""
+    if epilogue == "sum":
+        return raw
+    if epilogue == "half_n_log":
+        out = raw.clone()
+        S = raw[nparams]
+        out[:nparams] = raw[:nparams] * ((n_total / 2.0) * (1.0 / S))
+        out[nparams] = (n_total / 2.0) * torch.log(S)
+        return out
+    raise ValueError(epilogue)
+
+
+class ShardedObjective:
+    """local_eval(theta, raw_out) must fill raw_out (P+3 doubles, on `device`) with this
+    rank's raw sums for parameters `theta` (P doubles on `device`), asynchronously on
+    the current stream."""
+
+    def __init__(self, local_eval: Callable[[torch.Tensor, torch.Tensor], None], nparams: int,
+                 epilogue: str, n_total: int, device: torch.device, group=None):
+        self.local_eval, self.P, self.epilogue, self.n_total = local_eval, nparams, epilogue, n_total
+        self.device, self.group = device, group
+        self.raw = torch.zeros(nparams + 3, dtype=torch.float64, device=device)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def eval_raw(self, theta: torch.Tensor) -> torch.Tensor:
+        """-> all-reduced raw sums (device tensor; no host synchronisation)."""
+        self.local_eval(theta, self.raw)
+        if self.world > 1:
+            dist.all_reduce(self.raw, op=dist.ReduceOp.SUM, group=self.group)
+        return self.raw
+
+    def eval(self, theta: torch.Tensor):
+        """-> (f, grad) as a python float and a host tensor."""
+        out = apply_epilogue(self.eval_raw(theta), self.P, self.epilogue, float(self.n_total)).cpu()
+        return float(out[self.P]), out[: self.P].clone()
+
+
+def from_kernel(kernel, workload, device: torch.device, group=None) -> ShardedObjective:
+    """Wrap a configured host.Kernel bound to this rank's shard of `workload`."""
+    P = workload.nparams
+
+    def local_eval(theta: torch.Tensor, raw: torch.Tensor) -> None:
+        kernel.eval_device(theta.data_ptr(), P, raw.data_ptr(), want_grad=True, apply_epilogue=False)
+
+    n_total = int(workload.epilogue_n) if workload.epilogue_n else workload.size
+    return ShardedObjective(local_eval, P, workload.epilogue, n_total, device, group)

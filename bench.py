@@ -204,7 +204,7 @@ def main():
     # ------------------------------------------------------------------ our arm
     import torch
     import torch.distributed as dist
-    from ad4cl_b200 import host
+    from ad4cl_b200 import dist as D, host
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -236,12 +236,14 @@ def main():
     theta_dev = theta_host.to(dev)
     result_dev = torch.zeros(P + 3, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    epilogue_local = world == 1
+    sharded = D.from_kernel(k, w, dev) if world > 1 else None
 
     def step_device():
-        k.eval_device(theta_dev.data_ptr(), P, result_dev.data_ptr(), want_grad=True, apply_epilogue=epilogue_local)
-        if world > 1:
-            dist.all_reduce(result_dev)        # [grad..., S, ops, slots] summed over shards (sum epilogue only)
+        nonlocal result_dev
+        if world == 1:
+            k.eval_device(theta_dev.data_ptr(), P, result_dev.data_ptr(), want_grad=True, apply_epilogue=True)
+        else:   # local raw sums -> ONE all-reduce of P+3 doubles -> epilogue on every rank
+            result_dev = D.apply_epilogue(sharded.eval_raw(theta_dev), P, w.epilogue, float(n))
 
     def barrier():
         if world > 1:
