@@ -50,8 +50,35 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     return start, base + (1 if rank < rem else 0)
 
 
+def balanced_range(weights_per_block: list[int], block: int, n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard of rank `rank` whose WORK (not observation count) is 1/world of
+    the total: observation i costs weights_per_block[i // block].  Boundaries are at
+    observation granularity, so shards stay contiguous and the sum over ranks is exact."""
+    total = sum(wt * block for wt in weights_per_block)
+
+    def boundary(r: int) -> int:
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        target = total * r // world
+        acc = 0
+        for b, wt in enumerate(weights_per_block):
+            if acc + wt * block >= target:
+                return min(n, b * block + (target - acc) // wt)
+            acc += wt * block
+        return n
+
+    lo, hi = boundary(rank), boundary(rank + 1)
+    return lo, hi - lo
+
+
 def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 33, p: int = 10) -> Workload:
     start, count = shard_range(n, rank, world)
+    if name == "catch_at_age" and world > 1:
+        # tape length varies 4x with age: split by recorded slots, not by observation count
+        R = n // (synth.CAA_YEARS * synth.CAA_AGES)
+        start, count = balanced_range([sl for _, sl in _caa_per_cell()], R, n, rank, world)
     if name in ("linreg2_main", "linreg2_simple"):
         gen = synth.main_cpp_recipe if name == "linreg2_main" else synth.simple_cpp_recipe
         x, y, (a, b) = gen(n, start, count)

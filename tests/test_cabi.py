@@ -89,7 +89,9 @@ def test_workload_bookkeeping():
     assert sum(p.slots_total for p in parts) == w.slots_total
     assert np.array_equal(np.concatenate([p.d0 for p in parts]), w.d0)      # counter-based generators shard exactly
     assert all(np.array_equal(p.theta, w.theta) for p in parts)
-    assert [p.i1 for p in parts] == [0, 2667, 5334]
+    assert parts[0].i1 == 0 and all(parts[i].i1 + parts[i].size == parts[i + 1].i1 for i in range(2))
+    work = [p.slots_total for p in parts]
+    assert max(work) - min(work) <= 200 * 3      # balanced by recorded slots to within a few observations
     assert w.algorithmic_bytes() == 24 * w.slots_total + 8 * 8000 + 8 * 101
     for n, world in ((10, 3), (7, 8), (1000, 8)):
         rs = [W.shard_range(n, r, world) for r in range(world)]
