@@ -15,7 +15,8 @@
  *
  * Differences a kernel can observe, all deliberate:
  *   - ids are per-thread: independents keep the ids the host gave them
- *     (0..P-1), every temporary gets P + its position on this thread's tape.
+ *     (0..P-1), every temporary gets P + the index of its operator's last
+ *     operand slot on this thread's tape.
  *   - in-place operators (ad_plus_eq, ...) give the left-hand side a NEW id
  *     instead of re-using it (ad.cl:259); the sweep result is identical.
  *   - pad_init does not reserve a block: pad_* operators append in execution
@@ -129,7 +130,7 @@ AD4CL_DEV void ad_init_var_g(struct ad_gradient_structure* gs, struct ad_variabl
     if (gs->recording == 1) {
         ad4cl::tape_push(gs->tape, 0.0, 0, ad4cl::kEndFlag | ad4cl::kNopFlag);
         var->id = ad4cl::tape_close_op(gs->tape, 1);
-        gs->counter = gs->tape->nops;
+        gs->counter++;
     } else {
         var->id = 0;
     }
@@ -142,7 +143,7 @@ namespace ad4cl {
 AD4CL_DEV int record1(struct ad_gradient_structure* gs, double dx, int id) {
     tape_push(gs->tape, dx, id, kEndFlag);
     const int r = tape_close_op(gs->tape, 1);
-    gs->counter = gs->tape->nops;
+    gs->counter++;
     return r;
 }
 
@@ -150,7 +151,7 @@ AD4CL_DEV int record2(struct ad_gradient_structure* gs, double dx0, int id0, dou
     tape_push(gs->tape, dx0, id0, 0);
     tape_push(gs->tape, dx1, id1, kEndFlag);
     const int r = tape_close_op(gs->tape, 2);
-    gs->counter = gs->tape->nops;
+    gs->counter++;
     return r;
 }
 

@@ -122,10 +122,9 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     char* region;
     if (L.tape_in_smem) {
         region = reinterpret_cast<char*> (ad4cl_dyn_smem) + dbl_bytes + (size_t) warp * L.warp_region;
-        if (L.use_far) { /* the far bitmap must start clear */
-            unsigned* bits = reinterpret_cast<unsigned*> (region + (size_t) (L.cap_slots + kGuardRows) * kRowBytes
-                    + (size_t) L.cap_slots * kFarRowBytes);
-            for (int i = lane; i < (int) ((L.cap_slots + 31) / 32) * 32; i += 32) bits[i] = 0u;
+        if (L.use_far) { /* the far plane must start clear */
+            double* fa = reinterpret_cast<double*> (region + (size_t) (L.cap_slots + kGuardRows) * kRowBytes);
+            for (int i = lane; i < (int) (L.cap_slots + kGuardRows) * 32; i += 32) fa[i] = 0.0;
         }
     } else {
         region = L.arena + ((size_t) blockIdx.x * nw + warp) * L.warp_region;
@@ -192,7 +191,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     {
         const double s = warp_sum(sum);
         const double o = warp_sum((double) tape.total_ops);
-        const double k = warp_sum((double) (tape.total_slot_bytes / kRowBytes));
+        const double k = warp_sum((double) tape.total_slots);
         if (lane == 0) {
             red[(size_t) warp * ncols + P] = s;
             red[(size_t) warp * ncols + P + 1] = o;

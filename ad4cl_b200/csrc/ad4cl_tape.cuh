@@ -15,15 +15,16 @@
  *     memory per warp.  The stream lives in an HBM arena sized by RESIDENT
  *     warps (not by work-items) or in shared memory.
  *   - a slot is one (partial, operand id) pair: 12 bytes.  An operator with k
- *     variable operands pushes k slots; the result id is implicit (= position
- *     of the operator on this thread's tape + number of independents), the
- *     last slot of an operator carries END in the top bit of its id word.
+ *     variable operands pushes k slots; the result id is implicit (= number of
+ *     independents + the index of the operator's LAST slot on this thread's
+ *     tape), and that last slot carries END in the top bit of its id word.
  *     That is the 12k-bytes-per-op record of SURVEY.md 8(d).
  *   - the reverse sweep runs in the same kernel, right after the work-item's
  *     forward pass.  Adjoints of temporaries live in a shared-memory ring of W
- *     entries per thread (operands are almost always recent); an operand that
- *     is W or more operators old is detected at record time and routed to a
- *     "far" adjoint plane in the arena, flagged in a per-thread bitmap.
+ *     entries per thread indexed by slot index (operands are almost always
+ *     recent); an operand W or more slots old is detected at record time,
+ *     flagged FAR in its own slot and HAS_FAR in the END slot of the operator
+ *     that produced it, and its adjoint goes through a "far" plane in the arena.
  *   - adjoints of the independents (ids below first_temp) never touch the
  *     tape: they go to the accumulator the launch selected (ad4cl_entry.cuh).
  */
@@ -35,52 +36,52 @@
 
 namespace ad4cl {
 
-/* id word of a slot: [31] END  [30] NOP  [29] PARAM  [28] FAR  [27:0] payload.
-   payload = id of an independent (PARAM) or tape POSITION of a temporary. */
-constexpr int kEndFlag = (int) 0x80000000u; /* last slot of an operator */
-constexpr int kNopFlag = 0x40000000;        /* slot carries no partial (leaf variable) */
-constexpr int kParamFlag = 0x20000000;      /* operand is an independent */
-constexpr int kFarFlag = 0x10000000;        /* operand is a temporary `window` or more operators old */
-constexpr int kIdMask = 0x0FFFFFFF;
+/* id word of a slot:
+ *   [31] END      last slot of an operator (its index is the result's position)
+ *   [30] NOP      slot carries no partial (leaf variable)
+ *   [29] PARAM    operand is an independent; payload = its id
+ *   [28] FAR      operand is a temporary W or more slots old; payload = its position
+ *   [27] HAS_FAR  (END slots) the result of this operator received FAR contributions
+ *   [26:0] payload
+ */
+constexpr int kEndFlag = (int) 0x80000000u;
+constexpr int kNopFlag = 0x40000000;
+constexpr int kParamFlag = 0x20000000;
+constexpr int kFarFlag = 0x10000000;
+constexpr int kHasFarFlag = 0x08000000;
+constexpr int kIdMask = 0x07FFFFFF;
 constexpr int kNoId = -1;                   /* "no output written" */
 
 constexpr int kRowBytes = 384;              /* 32 lanes x (8 B partial + 4 B id word) */
 constexpr int kRowIdOffset = 256;
-constexpr int kFarRowBytes = 256;           /* far adjoints: 32 lanes x 8 B per operator */
-constexpr int kBitsRowBytes = 128;          /* far bitmap: 32 lanes x 4 B per 32 operators */
+constexpr int kFarRowBytes = 256;           /* far adjoints: 32 lanes x 8 B per slot index */
+constexpr int kGuardRows = 2;               /* an operator has at most 2 slots */
 
 enum Status : int {
     kOk = 0,
-    kErrTapeOverflow = 1,   /* more slots / operators than the arena column holds */
+    kErrTapeOverflow = 1,   /* more slots than the arena column holds */
     kErrWindow = 2,         /* far operand met while the far plane is disabled */
 };
 
 struct ThreadTape {
     char* cur;            /* address of this lane's partial in the next free row */
     char* begin;          /* row 0 */
-    char* end;            /* begin + capacity; two guard rows follow (an operator has <= 2 slots) */
+    char* end;            /* begin + capacity; kGuardRows guard rows follow */
     int id_off;           /* byte offset from a row's partial to its id word, this lane */
-    int nops;             /* operators recorded by the current work-item */
+    int next_id;          /* first_temp + index of the next free row */
     int first_temp;       /* number of independents: ids >= first_temp are tape positions */
-    int far_lim;          /* operand ids in [first_temp, far_lim] are `window` or more operators old */
-    int window;           /* W, a power of two */
+    int wm1;              /* W - 1, W a power of two */
+    int nops;             /* operators recorded by the current work-item (statistics) */
     char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
-    char* far_bits;       /* this lane's far bitmap column (row stride kBitsRowBytes) */
     int status;           /* sticky Status bits */
     long long total_ops;  /* statistics over all work-items of this thread */
-    long long total_slot_bytes;
+    long long total_slots;
 };
 
-constexpr int kGuardRows = 2;
-
-/* Bytes one warp needs in the arena for cap_slots slots (far planes are sized
-   by slots too: an operator has at least one slot). */
+/* Bytes one warp needs in the arena for cap_slots slots. */
 __host__ __device__ inline size_t warp_region_bytes(unsigned cap_slots, bool far) {
     size_t b = (size_t) (cap_slots + kGuardRows) * kRowBytes;
-    if (far) {
-        b += (size_t) cap_slots * kFarRowBytes;
-        b += (size_t) ((cap_slots + 31) / 32) * kBitsRowBytes;
-    }
+    if (far) b += (size_t) (cap_slots + kGuardRows) * kFarRowBytes;
     return (b + 127) & ~(size_t) 127;
 }
 
@@ -91,34 +92,23 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
     t.cur = t.begin;
     t.end = t.begin + (size_t) cap_slots * kRowBytes;
     t.id_off = kRowIdOffset - lane * 4;
-    t.nops = 0;
+    t.next_id = first_temp;
     t.first_temp = first_temp;
-    t.window = window;
-    t.far_lim = first_temp - window;
-    if (far) {
-        char* fa = warp_region + (size_t) (cap_slots + kGuardRows) * kRowBytes;
-        t.far_adj = fa + lane * 8;
-        t.far_bits = fa + (size_t) cap_slots * kFarRowBytes + lane * 4;
-    } else {
-        t.far_adj = nullptr;
-        t.far_bits = nullptr;
-    }
+    t.wm1 = window - 1;
+    t.nops = 0;
+    t.far_adj = far ? warp_region + (size_t) (cap_slots + kGuardRows) * kRowBytes + lane * 8 : nullptr;
     t.status = kOk;
     t.total_ops = 0;
-    t.total_slot_bytes = 0;
+    t.total_slots = 0;
 }
 
-/* An operand that is `window` or more operators old cannot use the ring: flag
-   it in the bitmap and clear its far adjoint on first use.  Cold path. */
-static __device__ __noinline__ int tape_note_far(char* far_adj, char* far_bits, int pos) {
-    if (far_adj == nullptr) return kErrWindow;
-    unsigned* word = reinterpret_cast<unsigned*> (far_bits + (size_t) (pos >> 5) * kBitsRowBytes);
-    const unsigned bit = 1u << (pos & 31);
-    const unsigned old = *word;
-    if (!(old & bit)) {
-        *word = old | bit;
-        *reinterpret_cast<double*> (far_adj + (size_t) pos * kFarRowBytes) = 0.0;
-    }
+/* An operand W or more slots old cannot use the ring: mark the END slot of the
+   operator that produced it.  The far plane is all zeros between work-items
+   (the sweep restores it), so nothing has to be cleared here, and the OR needs
+   no return value: it is issued as a fire-and-forget reduction. */
+__device__ __forceinline__ int tape_note_far(ThreadTape* t, int pos) {
+    if (t->far_adj == nullptr) return kErrWindow;
+    atomicOr(reinterpret_cast<int*> (t->begin + (size_t) pos * kRowBytes + t->id_off), kHasFarFlag);
     return kOk;
 }
 
@@ -134,33 +124,37 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
     } else {
         const int pos = id - t->first_temp;
         word = pos | flags;
-        if (id <= t->far_lim && !(flags & kNopFlag)) {
-            t->status |= tape_note_far(t->far_adj, t->far_bits, pos);
+        /* the operator being recorded ends at this row or the next one */
+        if (id + t->wm1 <= t->next_id && !(flags & kNopFlag)) {
+            t->status |= tape_note_far(t, pos);
             word |= kFarFlag;
         }
     }
     *reinterpret_cast<double*> (t->cur) = dx;
     *reinterpret_cast<int*> (t->cur + t->id_off) = word;
     t->cur += kRowBytes;
+    t->next_id++;
 }
 
-/* Close the operator whose `k` slots were just pushed; returns its result id. */
+/* Close the operator whose `k` slots were just pushed; returns its result id
+   (the position of its END slot). */
 __device__ __forceinline__ int tape_close_op(ThreadTape* t, int k) {
     if (t->cur > t->end) { /* does not fit: drop the operator, keep the pointer inside the guard */
         t->status |= kErrTapeOverflow;
         t->cur -= k * kRowBytes;
-        return t->first_temp + t->nops;
+        t->next_id -= k;
+        return t->next_id;
     }
-    t->far_lim++;
-    return t->first_temp + t->nops++;
+    t->nops++;
+    return t->next_id - 1;
 }
 
 /* Forget the current work-item's tape (the arena column is reused). */
 __device__ __forceinline__ void tape_rewind(ThreadTape& t) {
     t.total_ops += t.nops;
-    t.total_slot_bytes += t.cur - t.begin;
+    t.total_slots += t.next_id - t.first_temp;
     t.cur = t.begin;
-    t.far_lim -= t.nops;
+    t.next_id = t.first_temp;
     t.nops = 0;
 }
 
@@ -234,50 +228,41 @@ constexpr int kSweepUnroll = 4; /* rows fetched per batch; two batches are in fl
 /*
  * Reverse sweep of the current work-item's tape, seeded with 1 at `out_id`.
  * Restates the loop of ad4cl.h:786-797 (w = g[id]; g[id] = 0; g[operand] +=
- * w * dx) on the slot stream: the adjoint of the operator at position p is
- * popped from the ring when its END slot is met, and each slot scatters w * dx
- * to the ring (recent temporaries), the far plane (old temporaries) or the
- * accumulator (independents).  All lanes of the warp iterate together (tapes
- * of neighbouring work-items normally have identical shape).  The stream is
- * read kSweepUnroll rows at a time, one batch ahead of the batch being
- * processed, so the L2/HBM latency of a row is overlapped with the adjoint
- * arithmetic of the previous ones.
+ * w * dx) on the slot stream: the adjoint of an operator is popped from the
+ * ring when its END slot is met, and each slot scatters w * dx to the ring
+ * (recent temporaries), the far plane (old temporaries) or the accumulator
+ * (independents).  All lanes of the warp iterate together (tapes of
+ * neighbouring work-items normally have identical shape).  The stream is read
+ * kSweepUnroll rows at a time, one batch ahead of the batch being processed,
+ * so the L2/HBM latency of a row is overlapped with the adjoint arithmetic of
+ * the previous ones.
  */
 template <int MODE>
 __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T) {
     constexpr int U = kSweepUnroll;
-    const int wmask = t.window - 1;
+    const int wmask = t.wm1;
     const int id_off = t.id_off;
-    const bool far = t.far_adj != nullptr;
-    int p = t.nops;
-    const char* cur = t.cur;
-    unsigned rows = (unsigned) ((size_t) (t.cur - t.begin) / kRowBytes);
+    char* const far_adj = t.far_adj;
+    int rows = t.next_id - t.first_temp;
 
     /* seed d(out) = 1 */
     const int seed_pos = out_id - t.first_temp;
     sweep_param<MODE>(T, out_id >= 0 && out_id < t.first_temp, out_id, 1.0);
-    if (seed_pos >= 0 && seed_pos < p) {
-        /* operators recorded after `out` are dead; drop them when they could alias the seed's ring entry */
-        while (p - seed_pos > t.window) {
-            cur -= kRowBytes;
-            --rows;
-            if (*reinterpret_cast<const int*> (cur + id_off) < 0) --p;
-        }
+    if (seed_pos >= 0 && seed_pos < rows) {
+        /* rows recorded after `out` are dead; drop those that could alias the seed's ring entry */
+        if (rows - seed_pos > wmask) rows = seed_pos + wmask;
         sts_f64(T.ring + (unsigned) (seed_pos & wmask) * T.stride, 1.0);
     }
+    const char* cur = t.begin + (size_t) rows * kRowBytes;
 
     double w = 0.0;
-    unsigned bits = 0;
-    if (far && p > 0) bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) ((p - 1) >> 5) * kBitsRowBytes);
-    bool bits_dirty = false;
-
     /* the first batch takes the rows that do not fill a whole batch */
     double dx_now[U], dx_next[U];
     int id_now[U], id_next[U];
-    const unsigned head = rows & (U - 1);
+    const int head = rows & (U - 1);
 #pragma unroll
     for (int j = 0; j < U; j++) {
-        if ((unsigned) j < head) {
+        if (j < head) {
             const char* row = cur - (j + 1) * kRowBytes;
             dx_now[j] = *reinterpret_cast<const double*> (row);
             id_now[j] = *reinterpret_cast<const int*> (row + id_off);
@@ -287,7 +272,9 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
         }
     }
     cur -= (size_t) head * kRowBytes;
-    unsigned batches = rows / U; /* whole batches still in memory */
+    int idx = rows;            /* slot j of the batch in flight has index idx - 1 - j */
+    int next_idx = rows - head;
+    int batches = rows / U;    /* whole batches still in memory */
     bool more = true;
     while (__any_sync(0xffffffffu, more)) {
         const bool fetch = batches > 0;
@@ -310,21 +297,15 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
 #pragma unroll
         for (int j = 0; j < U; j++) {
             const int idw = id_now[j];
-            if (idw < 0) { /* END: this slot opens the next (older) operator */
-                --p;
-                const unsigned r = T.ring + (unsigned) (p & wmask) * T.stride;
+            if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
+                const int me = idx - 1 - j;
+                const unsigned r = T.ring + (unsigned) (me & wmask) * T.stride;
                 w = lds_f64(r);
                 sts_f64(r, 0.0);
-                if (far) {
-                    if ((bits >> (p & 31)) & 1u) {
-                        w += *reinterpret_cast<const double*> (t.far_adj + (size_t) p * kFarRowBytes);
-                        bits_dirty = true;
-                    }
-                    if ((p & 31) == 0) { /* leaving this bitmap word: clear it, fetch the next */
-                        if (bits_dirty) *reinterpret_cast<unsigned*> (t.far_bits + (size_t) (p >> 5) * kBitsRowBytes) = 0u;
-                        bits_dirty = false;
-                        if (p > 0) bits = *reinterpret_cast<const unsigned*> (t.far_bits + (size_t) ((p - 1) >> 5) * kBitsRowBytes);
-                    }
+                if (idw & kHasFarFlag) {
+                    double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
+                    w += *fa;
+                    *fa = 0.0;
                 }
             }
             const int payload = idw & kIdMask;
@@ -334,7 +315,7 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
                 const unsigned a = T.ring + (unsigned) (payload & wmask) * T.stride;
                 sts_f64(a, lds_f64(a) + c);
             } else if (cls == kFarFlag) {
-                if (far) *reinterpret_cast<double*> (t.far_adj + (size_t) payload * kFarRowBytes) += c;
+                if (far_adj != nullptr) *reinterpret_cast<double*> (far_adj + (size_t) payload * kFarRowBytes) += c;
             }
             sweep_param<MODE>(T, cls == kParamFlag, payload, c);
         }
@@ -343,10 +324,10 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
             dx_now[j] = dx_next[j];
             id_now[j] = id_next[j];
         }
+        idx = next_idx;
+        next_idx -= U;
         more = fetch;
     }
-    if (far && bits_dirty && p > 0)
-        *reinterpret_cast<unsigned*> (t.far_bits + (size_t) ((p - 1) >> 5) * kBitsRowBytes) = 0u;
 }
 
 } // namespace ad4cl

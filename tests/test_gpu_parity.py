@@ -75,9 +75,9 @@ def test_accumulator_modes_and_tape_tiers_agree(ctx, oracle_api, acc, tape):
     assert rel_err(g, ref["grad"]) <= RTOL
 
 
-@pytest.mark.parametrize("window,far", [(4, True), (16, True), (128, False)])
+@pytest.mark.parametrize("window,far", [(4, True), (16, True), (256, False)])
 def test_far_operands(ctx, oracle_api, window, far):
-    """catch_at_age re-uses M = exp(log M) up to ~110 operators later: with a small
+    """catch_at_age re-uses M = exp(log M) up to ~160 operand slots later: with a small
     ring those operands go through the far-adjoint plane."""
     w = W.describe("catch_at_age", 4000)
     ref, _ = oracle_eval(oracle_api, w, False)
