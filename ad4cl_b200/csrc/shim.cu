@@ -590,15 +590,14 @@ int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int referenc
     return fail(AD4CL_ERR_INVALID, "no built-in kernel named '%s'", name);
 }
 
-int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const char* entry,
-        const char* signature, const char* options, int reference_quirks, ad4cl_kernel** out) {
-    if (!ctx || !source || !entry || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+/* OpenCL prelude + user text + generated entry -> sm_100a cubin (no device needed) */
+static int compile_to_cubin(const char* source, const char* entry, const char* signature,
+        const char* options, int reference_quirks, std::vector<char>* cubin) {
+    if (!source || !entry) return fail(AD4CL_ERR_INVALID, "NULL argument");
     if (!signature_ok(signature)) return fail(AD4CL_ERR_INVALID, "bad signature '%s' (letters GSOVDIid, exactly one O)", signature ? signature : "");
     NvrtcApi& n = nvrtc();
     if (!n.ok) return fail(AD4CL_ERR_COMPILE, "libnvrtc could not be loaded: %s", dlerror());
-    if (!driver().ok) return fail(AD4CL_ERR_CUDA, "libcuda.so.1 could not be loaded");
 
-    /* translation unit = OpenCL prelude + user text + generated entry */
     std::string params, call;
     for (size_t i = 0; signature[i]; i++) {
         char nm[32];
@@ -638,7 +637,7 @@ int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const 
         }
     }
     std::vector<const char*> optv;
-    for (auto& s : opts) optv.push_back(s.c_str());
+    for (auto& o : opts) optv.push_back(o.c_str());
     rc = n.CompileProgram(prog, (int) optv.size(), optv.data());
     if (rc != 0) {
         size_t ls = 0;
@@ -650,14 +649,36 @@ int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const 
     }
     size_t cs = 0;
     n.GetCUBINSize(prog, &cs);
-    std::vector<char> cubin(cs);
-    n.GetCUBIN(prog, cubin.data());
+    cubin->resize(cs);
+    n.GetCUBIN(prog, cubin->data());
     n.DestroyProgram(&prog);
+    return AD4CL_OK;
+}
 
+int ad4cl_cuda_compile(const char* source, const char* entry, const char* signature, const char* options,
+        int reference_quirks, void** cubin, size_t* cubin_bytes) {
+    if (!cubin || !cubin_bytes) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    std::vector<char> bin;
+    int rc = compile_to_cubin(source, entry, signature, options, reference_quirks, &bin);
+    if (rc != AD4CL_OK) return rc;
+    *cubin = malloc(bin.size());
+    if (!*cubin) return fail(AD4CL_ERR_NOMEM, "malloc(%zu)", bin.size());
+    memcpy(*cubin, bin.data(), bin.size());
+    *cubin_bytes = bin.size();
+    return AD4CL_OK;
+}
+
+void ad4cl_cuda_free_host(void* p) { free(p); }
+
+int ad4cl_cuda_kernel_from_cubin(ad4cl_context* ctx, const void* cubin, size_t cubin_bytes, const char* entry,
+        const char* signature, int reference_quirks, ad4cl_kernel** out) {
+    if (!ctx || !cubin || !cubin_bytes || !entry || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (!signature_ok(signature)) return fail(AD4CL_ERR_INVALID, "bad signature '%s'", signature ? signature : "");
+    if (!driver().ok) return fail(AD4CL_ERR_CUDA, "libcuda.so.1 could not be loaded");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaFree(0)); /* make the primary context current for the driver API */
     ad4cl_kernel* k = new_kernel(ctx, entry, signature);
-    CUresult r = driver().cuModuleLoadData(&k->module, cubin.data());
+    CUresult r = driver().cuModuleLoadData(&k->module, cubin);
     if (r != CUDA_SUCCESS) {
         delete k;
         return fail(AD4CL_ERR_CUDA, "cuModuleLoadData failed: %d", (int) r);
@@ -672,6 +693,15 @@ int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const 
     k->cfg.reference_quirks = reference_quirks;
     *out = k;
     return AD4CL_OK;
+}
+
+int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const char* entry,
+        const char* signature, const char* options, int reference_quirks, ad4cl_kernel** out) {
+    if (!ctx || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    std::vector<char> bin;
+    int rc = compile_to_cubin(source, entry, signature, options, reference_quirks, &bin);
+    if (rc != AD4CL_OK) return rc;
+    return ad4cl_cuda_kernel_from_cubin(ctx, bin.data(), bin.size(), entry, signature, reference_quirks, out);
 }
 
 int ad4cl_cuda_kernel_free(ad4cl_kernel* k) {

@@ -75,6 +75,10 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_kernel_from_source.argtypes = [c_void_p, c_char_p, c_char_p, c_char_p, c_char_p, c_int,
                                                   POINTER(c_void_p)]
     lib.ad4cl_cuda_kernel_free.argtypes = [c_void_p]
+    lib.ad4cl_cuda_compile.argtypes = [c_char_p, c_char_p, c_char_p, c_char_p, c_int, POINTER(c_void_p), POINTER(c_size_t)]
+    lib.ad4cl_cuda_free_host.argtypes = [c_void_p]
+    lib.ad4cl_cuda_free_host.restype = None
+    lib.ad4cl_cuda_kernel_from_cubin.argtypes = [c_void_p, c_char_p, c_size_t, c_char_p, c_char_p, c_int, POINTER(c_void_p)]
     lib.ad4cl_cuda_kernel_set_arg_buffer.argtypes = [c_void_p, c_int, c_void_p]
     lib.ad4cl_cuda_kernel_set_arg_int.argtypes = [c_void_p, c_int, c_int]
     lib.ad4cl_cuda_kernel_set_arg_double.argtypes = [c_void_p, c_int, c_double]
@@ -96,6 +100,17 @@ lib = _load()
 def _check(rc: int) -> None:
     if rc != OK:
         raise Ad4clError(rc, (lib.ad4cl_cuda_last_error() or b"").decode(errors="replace"))
+
+
+def compile_source(source: str, entry: str, signature: str, options: str = "", quirks: bool = False) -> bytes:
+    """NVRTC-compile kernel text written against ad.cl to an sm_100a cubin. Needs no GPU."""
+    out, size = c_void_p(), c_size_t()
+    _check(lib.ad4cl_cuda_compile(source.encode(), entry.encode(), signature.encode(),
+                                  options.encode() if options else None, 1 if quirks else 0, byref(out), byref(size)))
+    try:
+        return ctypes.string_at(out.value, size.value)
+    finally:
+        lib.ad4cl_cuda_free_host(out)
 
 
 def builtin_kernels() -> dict[str, str]:
@@ -274,6 +289,12 @@ class Context:
         h = c_void_p()
         _check(lib.ad4cl_cuda_kernel_from_source(self._h, source.encode(), entry.encode(), signature.encode(),
                                                  options.encode() if options else None, 1 if quirks else 0, byref(h)))
+        return Kernel(self, h, entry)
+
+    def from_cubin(self, cubin: bytes, entry: str, signature: str, quirks: bool = False) -> Kernel:
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_kernel_from_cubin(self._h, cubin, len(cubin), entry.encode(), signature.encode(),
+                                                1 if quirks else 0, byref(h)))
         return Kernel(self, h, entry)
 
     def close(self) -> None:

@@ -134,6 +134,15 @@ const char* ad4cl_cuda_builtin_signature(int i);
  */
 int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const char* entry,
         const char* signature, const char* options, int reference_quirks, ad4cl_kernel** kernel);
+/*
+ * The two halves of _from_source: compile without touching a device (returns a malloc'd
+ * sm_100a cubin, release with ad4cl_cuda_free_host), and load a cubin produced earlier.
+ */
+int ad4cl_cuda_compile(const char* source, const char* entry, const char* signature, const char* options,
+        int reference_quirks, void** cubin, size_t* cubin_bytes);
+void ad4cl_cuda_free_host(void* p);
+int ad4cl_cuda_kernel_from_cubin(ad4cl_context* ctx, const void* cubin, size_t cubin_bytes, const char* entry,
+        const char* signature, int reference_quirks, ad4cl_kernel** kernel);
 int ad4cl_cuda_kernel_free(ad4cl_kernel* kernel);
 const char* ad4cl_cuda_kernel_signature(ad4cl_kernel* kernel);
 

@@ -1,0 +1,150 @@
+"""The JIT path (NVRTC): kernel text written against ad.cl is compiled at run time, the
+way the reference builds ad.cl + user file (test/admb/simple.cpp:138-175).
+
+CPU part: compilation only (NVRTC needs no GPU) -- including the reference's OWN
+simple.cl and matrixmul.cl, byte-for-byte unmodified, read from /root/reference.
+GPU part: the JIT-built kernels run and match the oracle; the reference's kernels are
+pre-compiled by __graft_entry__.build() into oracle/_ref/*.cubin (the sources cannot
+travel to the GPU box) and loaded with ad4cl_cuda_kernel_from_cubin.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from ad4cl_b200 import synth, workloads as W
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REF = "/root/reference"
+CUBINS = os.path.join(REPO, "oracle", "_ref")
+RTOL = 1e-12
+
+
+def rel_err(x, ref):
+    x, ref = np.atleast_1d(x), np.atleast_1d(ref)
+    return float(np.max(np.abs(x - ref) / np.maximum(np.maximum(np.abs(ref), np.abs(ref).max()), 1e-300)))
+
+
+def test_reference_kernels_compile_unmodified():
+    if not os.path.exists(os.path.join(REF, "ad.cl")):
+        pytest.skip("reference tree not mounted")
+    from ad4cl_b200 import host
+    for path, entry, sig in (("test/admb/simple.cl", "AD", "GSVVDDOi"),
+                             ("test/matrix/matrixmul.cl", "matrixMult", "GSVVOii")):
+        text = open(os.path.join(REF, path)).read()
+        for quirks in (True, False):
+            cubin = host.compile_source(text, entry, sig, quirks=quirks)
+            assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
+
+
+def test_objectives_compile_from_source_and_errors_carry_the_log():
+    from ad4cl_b200 import host
+    text = open(os.path.join(REPO, "ad4cl_b200", "kernels", "objectives.cl")).read()
+    assert host.compile_source(text, "catch_at_age", "GSVDDOiii")[:4] == b"\x7fELF"
+    with pytest.raises(host.Ad4clError) as e:
+        host.compile_source("__kernel void K(__global struct ad_gradient_structure* gs) { undeclared_fn(gs); }", "K", "GO")
+    assert e.value.code == host.ERR_COMPILE and "undeclared_fn" in str(e.value)
+    with pytest.raises(host.Ad4clError) as e:
+        host.compile_source(text, "catch_at_age", "GSVDDiii")      # no O in the signature
+    assert e.value.code == host.ERR_INVALID
+
+
+@pytest.mark.gpu
+def test_jit_kernel_matches_builtin_and_oracle(ctx, oracle_api):
+    from ad4cl_b200 import host
+    text = open(os.path.join(REPO, "ad4cl_b200", "kernels", "objectives.cl")).read()
+    w = W.describe("regression_logistic", 3001)
+    ref = oracle_api.best(False).eval_objective(w.kernel, w.theta, w.d0, w.d1, w.size, w.i0, w.i1, ops_per_item=w.max_ops)
+    kb = W.bind(ctx, w)
+    fb, gb = kb.eval(w.theta)
+    kb.free()
+    kj = ctx.from_source(text, "regression_logistic", "GSVDDOiii")
+    d0, d1 = ctx.buffer(w.d0), ctx.buffer(w.d1)
+    kj.set_args(None, None, host.params(0, w.nparams), d0, d1, None, w.size, w.i0, w.i1)
+    kj.configure(w.size, max_ops=w.max_ops, max_slots=w.max_slots)
+    fj, gj = kj.eval(w.theta)
+    kj.free()
+    assert rel_err(fj, ref["f"]) <= RTOL and rel_err(gj, ref["grad"]) <= RTOL
+    assert fj == fb and np.array_equal(gj, gb), "JIT and ahead-of-time builds of the same text disagree"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("quirks", [True, False], ids=["quirks", "fixed"])
+def test_reference_simple_cl_runs_on_the_cuda_runtime(ctx, oracle_api, quirks):
+    """test/admb/simple.cl, unmodified, on the main.cpp recipe; checked against the
+    reference's own evaluation of the same file on the CPU."""
+    from ad4cl_b200 import host
+    path = os.path.join(CUBINS, f"ref_simple_cl.{'q' if quirks else 'f'}.cubin")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/ref_simple_cl.*.cubin not built (run __graft_entry__.build() where the reference is mounted)")
+    n = 100003
+    x, y, (a, b) = synth.main_cpp_recipe(n)
+    k = ctx.from_cubin(open(path, "rb").read(), "AD", "GSVVDDOi", quirks=quirks)
+    k.set_args(None, None, host.params(0), host.params(1), ctx.buffer(x), ctx.buffer(y), None, n)
+    k.configure(n, max_ops=4, max_slots=6, local_size=64, epilogue="half_n_log")     # local 64: simple.cpp:235
+    f, g = k.eval([a, b])
+    ops = k.stats()["ops"]
+    k.free()
+    if oracle_api.have_reference():
+        ref = oracle_api.Reference(quirks).eval_simple(1, a, b, x, y, global_size=((n + 63) // 64 + 1) * 64)
+    else:
+        ref = oracle_api.Port(quirks).eval_objective("linreg2_p", [a, b], x, y, n, epilogue=1, ops_per_item=4)
+    assert rel_err(f, ref["f"]) <= RTOL and rel_err(g, ref["grad"]) <= RTOL
+    assert ops == 4 * n == ref["entries"] - n - 2
+
+
+def _matrix_case(ctx, oracle_api, kernel, n, quirks, acc):
+    from ad4cl_b200 import host
+    A, B = synth.msvcrt_rand_matrices(n)
+    kernel.set_args(None, None, host.params(0, n * n), host.params(n * n, n * n), None, n, n)
+    kernel.configure((n, n), max_ops=2 * n + 1, max_slots=4 * n + 1, local_size=(16, 16), acc=acc)
+    f, g = kernel.eval(np.concatenate([A, B]))
+    st = kernel.stats()
+    kernel.free()
+    orc = oracle_api.Reference(quirks) if oracle_api.have_reference() else oracle_api.Port(quirks)
+    ref = orc.matrix(n, A, B, want_grad=True) if orc.kind == "port" else orc.matrix(n, A, B, variant=-1, want_grad=True)
+    assert rel_err(f, ref["C"].sum()) <= RTOL
+    assert rel_err(g, ref["grad"]) <= RTOL
+    # n^2 (leaf + 2n operators); the reference's count has n^2 host-sum entries in place of the leaves
+    assert int(st["ops"]) == n * n * (2 * n + 1) == ref["entries"]
+    return f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("acc", ["warp", "global"])
+@pytest.mark.parametrize("quirks", [True, False], ids=["quirks", "fixed"])
+def test_matrix_product_gradient(ctx, oracle_api, quirks, acc):
+    """config 2 (tape path): d(sum C)/d(A,B), 2 n^2 independents, 2-D NDRange (n, n) local (16, 16)."""
+    _matrix_case(ctx, oracle_api, ctx.builtin("matrix_product", quirks=quirks), 48, quirks, acc)
+
+
+@pytest.mark.gpu
+def test_reference_matrixmul_cl_runs_on_the_cuda_runtime(ctx, oracle_api):
+    path = os.path.join(CUBINS, "ref_matrixmul_cl.q.cubin")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/ref_matrixmul_cl.q.cubin not built")
+    k = ctx.from_cubin(open(path, "rb").read(), "matrixMult", "GSVVOii", quirks=True)
+    _matrix_case(ctx, oracle_api, k, 32, True, "warp")
+
+
+@pytest.mark.gpu
+def test_matrix_golden_256(ctx):
+    """The reference's golden file test/matrix/host.txt: sum of the printed C vs our sum C
+    (6 printed digits per element), and the tape length on its last line."""
+    from ad4cl_b200 import host
+    z = np.load(os.path.join(REPO, "tests", "golden", "matrix256_host_txt.npz"))
+    n = 256
+    A, B = synth.msvcrt_rand_matrices(n)
+    k = ctx.builtin("matrix_product")
+    k.set_args(None, None, host.params(0, n * n), host.params(n * n, n * n), None, n, n)
+    k.configure((n, n), max_ops=2 * n + 1, max_slots=4 * n + 1, local_size=(16, 16), acc="global")
+    f, g = k.eval(np.concatenate([A, B]))
+    st = k.stats()
+    k.free()
+    assert abs(f - z["C"].sum()) / z["C"].sum() < 1e-6
+    # matrix_mul.cpp:272 prints stack_current after the host sum: 2n entries per element + n^2 sum
+    # entries; ours records the n^2 leaf accumulators of ad_init_var_g instead of the host sum
+    assert int(st["ops"]) == int(z["entries"]) == 33619968
+    gA = np.repeat(B.reshape(n, n).sum(axis=1)[None, :], n, axis=0).ravel()
+    gB = np.repeat(A.reshape(n, n).sum(axis=0)[:, None], n, axis=1).ravel()
+    assert rel_err(g, np.concatenate([gA, gB])) <= RTOL
