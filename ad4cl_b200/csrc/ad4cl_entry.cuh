@@ -39,7 +39,7 @@ struct LaunchInfo {
     unsigned cap_slots;     /* per-thread tape capacity (operand slots) */
     char* arena;            /* HBM arena: one warp region per resident warp */
     unsigned long long warp_region;  /* bytes per warp region */
-    double* partials;       /* [gridDim.x][ncols], ncols = nparams + 3 */
+    double* partials;       /* [gridDim.x][ncols]; ncols = nparams + 3, or 3 with kAccGlobal: [grad..., sum, ops, slots] */
     double* global_grad;    /* kAccGlobal target, else null */
     int* status;            /* OR of Status bits */
 };
@@ -87,7 +87,7 @@ __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int w
     size_t d = (size_t) window * block;
     if (acc_mode == kAccThread) d += (size_t) nparams * block;
     if (acc_mode == kAccWarp) d += (size_t) nw * nparams;
-    d += (size_t) nw * (nparams + 3);
+    d += (size_t) nw * ((acc_mode == kAccGlobal ? 0 : nparams) + 3);
     size_t bytes = d * sizeof (double);
     bytes = (bytes + 127) & ~(size_t) 127;
     if (tape_in_smem) bytes += (size_t) nw * warp_region_bytes(cap_slots, far);
@@ -102,7 +102,8 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     const int warp = tid >> 5;
     const int nw = B >> 5;
     const int P = L.nparams;
-    const int ncols = P + 3;
+    const int PR = L.acc_mode == kAccGlobal ? 0 : P;   /* gradient columns that go through the block reduction */
+    const int ncols = PR + 3;
 
     double* smem = reinterpret_cast<double*> (ad4cl_dyn_smem);
     double* ring = smem;
@@ -177,14 +178,12 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 
     /* ---- block reduction: warp shuffles, then warps in fixed order ---- */
     __syncthreads();
-    for (int p = 0; p < P; p++) {
+    for (int p = 0; p < PR; p++) {
         double v;
         if (L.acc_mode == kAccThread) {
             v = warp_sum(thread_acc[(size_t) p * B + tid]);
-        } else if (L.acc_mode == kAccWarp) {
-            v = warp_acc[(size_t) warp * P + p];
         } else {
-            v = 0.0; /* already in global_grad */
+            v = warp_acc[(size_t) warp * P + p];
         }
         if (lane == 0) red[(size_t) warp * ncols + p] = v;
     }
@@ -193,9 +192,9 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         const double o = warp_sum((double) tape.total_ops);
         const double k = warp_sum((double) tape.total_slots);
         if (lane == 0) {
-            red[(size_t) warp * ncols + P] = s;
-            red[(size_t) warp * ncols + P + 1] = o;
-            red[(size_t) warp * ncols + P + 2] = k;
+            red[(size_t) warp * ncols + PR] = s;
+            red[(size_t) warp * ncols + PR + 1] = o;
+            red[(size_t) warp * ncols + PR + 2] = k;
         }
     }
     const int st = __reduce_or_sync(0xffffffffu, tape.status);

@@ -7,23 +7,23 @@
 #include "ad4cl_tape.cuh"
 
 /*
- * Second stage: result[c] = sum over blocks (in block order) of partials[b][c].
+ * Second stage: result[first_col + c] = sum over blocks (in block order) of partials[b][c].
  * One block per column; a fixed strided pass then a fixed tree, so the value
  * does not depend on scheduling.  Optional scalar epilogue of the reference
  * (simple.cpp:365, main.cpp:417):  f = (n/2) log S, grad *= (n/2)/S.
- *   result layout: [grad[0..P-1], f, total ops, total slots]
+ *   partials columns: [grad (ngrad of them), S, total ops, total slots]
+ *   result layout   : [grad[0..P-1], f, total ops, total slots], written from first_col on
  */
 extern "C" __global__ void __launch_bounds__(256) ad4cl_reduce_partials(
-        const double* __restrict__ partials, int nblocks, int ncols, int nparams,
-        const double* __restrict__ global_grad, int epilogue, double n_obs,
-        double* __restrict__ result) {
+        const double* __restrict__ partials, int nblocks, int ncols, int ngrad, int first_col,
+        int epilogue, double n_obs, double* __restrict__ result) {
     __shared__ double scratch[2][8];
     const int c = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double v = 0.0, s = 0.0;
     for (int b = tid; b < nblocks; b += 256) {
         v += partials[(size_t) b * ncols + c];
-        s += partials[(size_t) b * ncols + nparams];
+        s += partials[(size_t) b * ncols + ngrad];
     }
     v = ad4cl::warp_sum(v);
     s = ad4cl::warp_sum(s);
@@ -38,12 +38,35 @@ extern "C" __global__ void __launch_bounds__(256) ad4cl_reduce_partials(
             tv += scratch[0][w];
             ts += scratch[1][w];
         }
-        if (c < nparams && global_grad != nullptr) tv = global_grad[c];
         if (epilogue == 1) {
-            if (c < nparams) tv *= (n_obs / 2.0) * (1.0 / ts);
-            else if (c == nparams) tv = (n_obs / 2.0) * log(ts);
+            if (c < ngrad) tv *= (n_obs / 2.0) * (1.0 / ts);
+            else if (c == ngrad) tv = (n_obs / 2.0) * log(ts);
         }
-        result[c] = tv;
+        result[first_col + c] = tv;
     }
 }
 
+/*
+ * kAccGlobal: the gradient was accumulated by fp64 RED into global_grad[P]; copy it
+ * into the result (scaled by the epilogue, whose S every block re-derives from the
+ * partials in the same fixed order).
+ */
+extern "C" __global__ void __launch_bounds__(256) ad4cl_finish_global_grad(
+        const double* __restrict__ global_grad, int nparams, const double* __restrict__ partials,
+        int nblocks, int epilogue, double n_obs, double* __restrict__ result) {
+    double scale = 1.0;
+    if (epilogue == 1) {
+        __shared__ double scratch[8];
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        double s = 0.0;
+        for (int b = tid; b < nblocks; b += 256) s += partials[(size_t) b * 3];
+        s = ad4cl::warp_sum(s);
+        if (lane == 0) scratch[warp] = s;
+        __syncthreads();
+        double ts = 0.0;
+        for (int w = 0; w < 8; w++) ts += scratch[w];
+        scale = (n_obs / 2.0) * (1.0 / ts);
+    }
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < nparams) result[i] = global_grad[i] * scale;
+}

@@ -30,6 +30,7 @@ extern "C" const ad4cl_builtin_row ad4cl_builtin_table_quirks[];
 extern "C" const char* const ad4cl_embedded_header_names[];
 extern "C" const char* const ad4cl_embedded_header_texts[];
 extern "C" const int ad4cl_embedded_header_count;
+extern "C" const char ad4cl_embedded_header_hash[];
 
 namespace {
 
@@ -281,7 +282,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     k->data_items = c.global_size[0] * (c.global_size[1] > 0 ? c.global_size[1] : 1);
 
     int acc = c.acc_mode;
-    if (acc == AD4CL_ACC_AUTO) acc = nparams <= 16 ? AD4CL_ACC_THREAD : (nparams <= 4096 ? AD4CL_ACC_WARP : AD4CL_ACC_GLOBAL);
+    if (acc == AD4CL_ACC_AUTO) acc = nparams <= 16 ? AD4CL_ACC_THREAD : (nparams <= 512 ? AD4CL_ACC_WARP : AD4CL_ACC_GLOBAL);
     const int max_ops = std::max(c.max_ops, 1);
     const unsigned cap_slots = (unsigned) (c.max_slots > 0 ? c.max_slots : 2 * max_ops);
     const bool far = c.far_plane != 0;
@@ -307,10 +308,11 @@ int prepare(ad4cl_kernel* k, int nparams) {
     const size_t region = ad4cl::warp_region_bytes(cap_slots, far);
     const size_t arena_bytes = tier == AD4CL_TAPE_SHARED ? 0 : (size_t) grid * (block / 32) * region;
     const int ncols = nparams + 3;
+    const int pcols = (acc == AD4CL_ACC_GLOBAL ? 0 : nparams) + 3; /* columns of the per-block partials */
 
     CUDA_TRY(cudaMalloc(&k->params_dev, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
     CUDA_TRY(cudaMalloc(&k->theta_dev, sizeof (double) * (size_t) std::max(nparams, 1)));
-    CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) grid * ncols));
+    CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) grid * pcols));
     CUDA_TRY(cudaMalloc(&k->result_dev, sizeof (double) * (size_t) ncols));
     CUDA_TRY(cudaMalloc(&k->status_dev, sizeof (int)));
     CUDA_TRY(cudaMemset(k->status_dev, 0, sizeof (int)));
@@ -386,7 +388,7 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
     }
     ad4cl::LaunchInfo L = k->L;
     L.recording = want_gradient ? 1 : 0;
-    if (k->global_grad && want_gradient)
+    if (k->global_grad)
         CUDA_TRY(cudaMemsetAsync(k->global_grad, 0, sizeof (double) * (size_t) std::max(P, 1), st));
 
     /* marshal: LaunchInfo first, then the user kernel's non-runtime parameters in order */
@@ -441,10 +443,16 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
         if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuLaunchKernel(%s) failed: %d", k->name.c_str(), (int) r);
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
-    const int ncols = P + 3;
     const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
-    ad4cl_reduce_partials<<<ncols, 256, 0, st>>>(k->partials, k->grid, ncols, P,
-            want_gradient ? k->global_grad : nullptr, apply_epilogue ? k->cfg.epilogue : 0, n_obs, result_dev);
+    const int epi = apply_epilogue ? k->cfg.epilogue : 0;
+    if (k->global_grad) {
+        ad4cl_reduce_partials<<<3, 256, 0, st>>>(k->partials, k->grid, 3, 0, P, epi, n_obs, result_dev);
+        if (P > 0)
+            ad4cl_finish_global_grad<<<(P + 255) / 256, 256, 0, st>>>(k->global_grad, P, k->partials, k->grid,
+                    epi, n_obs, result_dev);
+    } else {
+        ad4cl_reduce_partials<<<P + 3, 256, 0, st>>>(k->partials, k->grid, P + 3, P, 0, epi, n_obs, result_dev);
+    }
     CUDA_TRY(cudaGetLastError());
     return AD4CL_OK;
 }
@@ -469,6 +477,8 @@ int status_to_error(ad4cl_kernel* k, int st) {
 extern "C" {
 
 const char* ad4cl_cuda_last_error(void) { return g_last_error.c_str(); }
+
+const char* ad4cl_cuda_device_abi(void) { return ad4cl_embedded_header_hash; }
 
 int ad4cl_cuda_init(int device, ad4cl_context** out) {
     if (!out) return fail(AD4CL_ERR_INVALID, "ctx is NULL");

@@ -54,6 +54,7 @@ def _load() -> ctypes.CDLL:
             "ad4cl_b200 has no CPU implementation to fall back to.")
     lib = ctypes.CDLL(LIB_PATH)
     lib.ad4cl_cuda_last_error.restype = c_char_p
+    lib.ad4cl_cuda_device_abi.restype = c_char_p
     lib.ad4cl_cuda_stream.restype = c_void_p
     lib.ad4cl_cuda_stream.argtypes = [c_void_p]
     lib.ad4cl_cuda_use_stream.argtypes = [c_void_p, c_void_p]
@@ -100,6 +101,11 @@ lib = _load()
 def _check(rc: int) -> None:
     if rc != OK:
         raise Ad4clError(rc, (lib.ad4cl_cuda_last_error() or b"").decode(errors="replace"))
+
+
+def device_abi() -> str:
+    """Hash of the device headers the library embeds; cubins are only valid for the same hash."""
+    return lib.ad4cl_cuda_device_abi().decode()
 
 
 def compile_source(source: str, entry: str, signature: str, options: str = "", quirks: bool = False) -> bytes:

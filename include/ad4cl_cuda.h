@@ -104,6 +104,9 @@ typedef struct ad4cl_eval_stats {
 int ad4cl_cuda_init(int device, ad4cl_context** ctx);
 int ad4cl_cuda_shutdown(ad4cl_context* ctx);
 const char* ad4cl_cuda_last_error(void);
+/* identifies the device-side headers this library was built with; a cubin from ad4cl_cuda_compile
+   is only valid for the library that reports the same string */
+const char* ad4cl_cuda_device_abi(void);
 /* the CUDA stream of the context, as a cudaStream_t cast to void* */
 void* ad4cl_cuda_stream(ad4cl_context* ctx);
 /* run on a caller-owned stream (e.g. torch's current stream); NULL restores the context's own */
