@@ -94,7 +94,7 @@ __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int w
     return bytes;
 }
 
-template <typename Body>
+template <int MODE, typename Body>
 __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) {
     const int B = blockDim.x;
     const int tid = threadIdx.x;
@@ -102,21 +102,21 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     const int warp = tid >> 5;
     const int nw = B >> 5;
     const int P = L.nparams;
-    const int PR = L.acc_mode == kAccGlobal ? 0 : P;   /* gradient columns that go through the block reduction */
+    const int PR = MODE == kAccGlobal ? 0 : P;   /* gradient columns that go through the block reduction */
     const int ncols = PR + 3;
 
     double* smem = reinterpret_cast<double*> (ad4cl_dyn_smem);
     double* ring = smem;
     double* thread_acc = ring + (size_t) L.window * B;
-    double* warp_acc = thread_acc + (L.acc_mode == kAccThread ? (size_t) P * B : 0);
-    double* red = warp_acc + (L.acc_mode == kAccWarp ? (size_t) nw * P : 0);
+    double* warp_acc = thread_acc + (MODE == kAccThread ? (size_t) P * B : 0);
+    double* red = warp_acc + (MODE == kAccWarp ? (size_t) nw * P : 0);
     size_t dbl_bytes = (size_t) ((red + (size_t) nw * ncols) - smem) * sizeof (double);
     dbl_bytes = (dbl_bytes + 127) & ~(size_t) 127;
 
     for (int i = tid; i < L.window * B; i += B) ring[i] = 0.0;
-    if (L.acc_mode == kAccThread)
+    if (MODE == kAccThread)
         for (int i = tid; i < P * B; i += B) thread_acc[i] = 0.0;
-    if (L.acc_mode == kAccWarp)
+    if (MODE == kAccWarp)
         for (int i = tid; i < nw * P; i += B) warp_acc[i] = 0.0;
     if (tid == 0) ad4cl_local_size0 = L.l0;
 
@@ -168,11 +168,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         body(&gs, &outv - item);
         sum += outv.value;
         /* a thread whose tape overflowed skips the sweep (the host reports the error) */
-        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
-            if (L.acc_mode == kAccWarp) tape_sweep<kAccWarp>(tape, outv.id, T);
-            else if (L.acc_mode == kAccThread) tape_sweep<kAccThread>(tape, outv.id, T);
-            else tape_sweep<kAccGlobal>(tape, outv.id, T);
-        }
+        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) tape_sweep<MODE>(tape, outv.id, T);
         tape_rewind(tape);
     }
 
@@ -180,7 +176,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     __syncthreads();
     for (int p = 0; p < PR; p++) {
         double v;
-        if (L.acc_mode == kAccThread) {
+        if (MODE == kAccThread) {
             v = warp_sum(thread_acc[(size_t) p * B + tid]);
         } else {
             v = warp_acc[(size_t) warp * P + p];
@@ -223,15 +219,21 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 #ifndef AD4CL_ENTRY_SUFFIX
 #define AD4CL_ENTRY_SUFFIX /* the two ahead-of-time builds of one kernel need distinct symbols */
 #endif
-#define AD4CL_CAT3_(a, b, c) a##b##c
-#define AD4CL_CAT3(a, b, c) AD4CL_CAT3_(a, b, c)
-#define AD4CL_ENTRY_NAME(NAME) AD4CL_CAT3(NAME, __entry, AD4CL_ENTRY_SUFFIX)
-#define AD4CL_OBJECTIVE_ENTRY(NAME, PARAMS, ARGS)                                         \
+#define AD4CL_CAT4_(a, b, c, d) a##b##c##d
+#define AD4CL_CAT4(a, b, c, d) AD4CL_CAT4_(a, b, c, d)
+/* one __global__ function per accumulator mode, so a launch only brings the code of
+   the sweep it uses into the instruction cache: NAME__entry<suffix>_m0 / _m1 / _m2 */
+#define AD4CL_ENTRY_NAME(NAME, MODE) AD4CL_CAT4(NAME, __entry, AD4CL_ENTRY_SUFFIX, _m##MODE)
+#define AD4CL_OBJECTIVE_ENTRY_MODE(NAME, MODE, PARAMS, ARGS)                               \
     extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK, AD4CL_MIN_BLOCKS)        \
-    AD4CL_ENTRY_NAME(NAME)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {              \
-        ad4cl::run_objective(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out) { \
+    AD4CL_ENTRY_NAME(NAME, MODE)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
+        ad4cl::run_objective<MODE>(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out) { \
             struct ad_entry* gradient_stack = nullptr;                                     \
             (void) gradient_stack;                                                         \
             NAME(AD4CL_UNPAREN ARGS);                                                      \
         });                                                                                \
     }
+#define AD4CL_OBJECTIVE_ENTRY(NAME, PARAMS, ARGS)                                         \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 0, PARAMS, ARGS)                                      \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 1, PARAMS, ARGS)                                      \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 2, PARAMS, ARGS)

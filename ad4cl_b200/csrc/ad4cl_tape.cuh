@@ -223,7 +223,13 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
     }
 }
 
-constexpr int kSweepUnroll = 4; /* rows fetched per batch; two batches are in flight */
+#ifndef AD4CL_FAR_RED
+#define AD4CL_FAR_RED 0
+#endif
+#ifndef AD4CL_SWEEP_UNROLL
+#define AD4CL_SWEEP_UNROLL 4
+#endif
+constexpr int kSweepUnroll = AD4CL_SWEEP_UNROLL; /* rows fetched per batch; two batches are in flight */
 
 /*
  * Reverse sweep of the current work-item's tape, seeded with 1 at `out_id`.
@@ -329,5 +335,4 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
         more = fetch;
     }
 }
-
 } // namespace ad4cl

@@ -40,7 +40,8 @@ AD4CL_OBJECTIVE_ENTRY(matrix_elementwise,
     (struct ad_variable* A, struct ad_variable* B, int width, int op),
     (gs, gradient_stack, A, B, out, width, op))
 
-#define ROW(NAME, SIG) {#NAME, (const void*) &AD4CL_ENTRY_NAME(NAME), SIG}
+#define ROW(NAME, SIG) {#NAME, {(const void*) &AD4CL_ENTRY_NAME(NAME, 0), (const void*) &AD4CL_ENTRY_NAME(NAME, 1), \
+                             (const void*) &AD4CL_ENTRY_NAME(NAME, 2)}, SIG}
 extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(linreg2_g, "GSVVDDOi"),
     ROW(linreg2_p, "GSVVDDOi"),
@@ -51,5 +52,5 @@ extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(op_zoo, "GSVDDOiii"),
     ROW(matrix_product, "GSVVOii"),
     ROW(matrix_elementwise, "GSVVOii"),
-    {nullptr, nullptr, nullptr},
+    {nullptr, {nullptr, nullptr, nullptr}, nullptr},
 };

@@ -169,8 +169,10 @@ struct ad4cl_buffer {
 struct ad4cl_kernel {
     ad4cl_context* ctx = nullptr;
     std::string name, signature;
-    const void* entry = nullptr;   /* ahead-of-time kernel (runtime API handle) */
+    const void* entries[3] = {nullptr, nullptr, nullptr};  /* ahead-of-time kernel, per accumulator mode */
+    const void* entry = nullptr;   /* the one selected by prepare() */
     CUmodule module = nullptr;     /* NVRTC kernel */
+    CUfunction functions[3] = {nullptr, nullptr, nullptr};
     CUfunction function = nullptr;
     std::vector<Arg> args;
     ad4cl_kernel_config cfg{};
@@ -240,7 +242,7 @@ ad4cl_kernel* new_kernel(ad4cl_context* ctx, const char* name, const char* sig) 
 }
 
 int occupancy(ad4cl_kernel* k, int block, size_t smem, int* blocks) {
-    if (k->entry) {
+    if (!k->module) {
         if (smem > 48 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(k->entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k->entry, block, smem));
@@ -283,6 +285,8 @@ int prepare(ad4cl_kernel* k, int nparams) {
 
     int acc = c.acc_mode;
     if (acc == AD4CL_ACC_AUTO) acc = nparams <= 16 ? AD4CL_ACC_THREAD : (nparams <= 512 ? AD4CL_ACC_WARP : AD4CL_ACC_GLOBAL);
+    if (k->module) k->function = k->functions[acc];
+    else k->entry = k->entries[acc];
     const int max_ops = std::max(c.max_ops, 1);
     const unsigned cap_slots = (unsigned) (c.max_slots > 0 ? c.max_slots : 2 * max_ops);
     const bool far = c.far_plane != 0;
@@ -435,7 +439,7 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
         k->prof_used++;
         CUDA_TRY(cudaEventRecord(pe0, st));
     }
-    if (k->entry) {
+    if (!k->module) {
         CUDA_TRY(cudaLaunchKernel(k->entry, dim3(k->grid), dim3(k->block), argv.data(), k->smem, st));
     } else {
         CUresult r = driver().cuLaunchKernel(k->function, k->grid, 1, 1, k->block, 1, 1, (unsigned) k->smem,
@@ -591,7 +595,7 @@ int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int referenc
     for (const ad4cl_builtin_row* r = tab; r->name; r++) {
         if (strcmp(r->name, name) == 0) {
             ad4cl_kernel* k = new_kernel(ctx, name, r->signature);
-            k->entry = r->entry;
+            for (int m = 0; m < 3; m++) k->entries[m] = r->entry[m];
             k->cfg.reference_quirks = reference_quirks;
             *out = k;
             return AD4CL_OK;
@@ -693,12 +697,14 @@ int ad4cl_cuda_kernel_from_cubin(ad4cl_context* ctx, const void* cubin, size_t c
         delete k;
         return fail(AD4CL_ERR_CUDA, "cuModuleLoadData failed: %d", (int) r);
     }
-    std::string fn = std::string(entry) + "__entry";
-    r = driver().cuModuleGetFunction(&k->function, k->module, fn.c_str());
-    if (r != CUDA_SUCCESS) {
-        driver().cuModuleUnload(k->module);
-        delete k;
-        return fail(AD4CL_ERR_CUDA, "cuModuleGetFunction(%s) failed: %d", fn.c_str(), (int) r);
+    for (int m = 0; m < 3; m++) {
+        std::string fn = std::string(entry) + "__entry_m" + std::to_string(m);
+        r = driver().cuModuleGetFunction(&k->functions[m], k->module, fn.c_str());
+        if (r != CUDA_SUCCESS) {
+            driver().cuModuleUnload(k->module);
+            delete k;
+            return fail(AD4CL_ERR_CUDA, "cuModuleGetFunction(%s) failed: %d", fn.c_str(), (int) r);
+        }
     }
     k->cfg.reference_quirks = reference_quirks;
     *out = k;

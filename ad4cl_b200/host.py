@@ -21,7 +21,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_longlon
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libad4cl_cuda.so")
+LIB_PATH = os.environ.get("AD4CL_CUDA_LIB", os.path.join(_HERE, "libad4cl_cuda.so"))  # override: A/B builds
 
 OK, ERR_CUDA, ERR_INVALID, ERR_TAPE_OVERFLOW, ERR_WINDOW, ERR_COMPILE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 ACC = {"auto": -1, "thread": 0, "warp": 1, "global": 2}
