@@ -214,7 +214,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
  */
 #define AD4CL_UNPAREN(...) __VA_ARGS__
 #ifndef AD4CL_MIN_BLOCKS
-#define AD4CL_MIN_BLOCKS 4 /* 4 x 256 threads per SM: caps the entry at 64 registers */
+#define AD4CL_MIN_BLOCKS 3 /* 3 x 256 threads per SM = 80 registers: measured faster than 4 (64 registers spill and rematerialise) */
 #endif
 #ifndef AD4CL_ENTRY_SUFFIX
 #define AD4CL_ENTRY_SUFFIX /* the two ahead-of-time builds of one kernel need distinct symbols */

@@ -31,6 +31,7 @@ class Workload:
     slots_total: int = 0
     input_bytes: int = 0      # data bytes read once per evaluation
     linreg2: bool = False     # (a, b) passed as two separate V arguments (simple.cl signature)
+    matrix: int = 0           # n of an n x n matrix kernel (A, B as 2 n^2 independents, 2-D NDRange)
     extra: dict = field(default_factory=dict)
 
     @property
@@ -106,6 +107,17 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
         return Workload(name, name, theta, x, None, count, i0=steps, i1=p, max_ops=ops, max_slots=slots,
                         ops_total=ops * count, slots_total=slots * count, input_bytes=8 * count,
                         extra={"steps": steps})
+    if name in ("matrix_product", "matrix_elementwise"):
+        # config 2: test/matrix (matrix_mul.cpp:84-90 inputs); n is the matrix dimension here
+        A, B = synth.msvcrt_rand_matrices(n)
+        op = steps if name == "matrix_elementwise" else 0      # elementwise op selector rides on `steps`
+        if name == "matrix_product":
+            ops, slots = 2 * n + 1, 4 * n + 1
+        else:
+            ops, slots = {0: (1, 2), 1: (1, 2), 2: (1, 2), 3: (1, 1), 4: (2, 2)}[op]
+        return Workload(name, name, np.concatenate([A, B]), None, None, n * n, i0=n, i1=op if name == "matrix_elementwise" else n,
+                        max_ops=ops, max_slots=slots, ops_total=ops * n * n, slots_total=slots * n * n,
+                        input_bytes=2 * n * n * 16, matrix=n)
     if name == "op_zoo":
         d0, theta = synth.op_zoo(n)
         return Workload(name, name, theta, d0[start:start + count], None, count, max_ops=48, max_slots=96,
@@ -167,6 +179,13 @@ def bind(ctx, w: Workload, *, quirks: bool = False, **cfg):
     k = ctx.builtin(w.kernel, quirks=quirks)
     d0 = ctx.buffer(w.d0) if w.d0 is not None else None
     d1 = ctx.buffer(w.d1) if w.d1 is not None else None
+    if w.matrix:
+        n = w.matrix
+        k.set_args(None, None, host.params(0, n * n), host.params(n * n, n * n), None, w.i0, w.i1)
+        opts = dict(max_ops=w.max_ops, max_slots=w.max_slots, local_size=(16, 16), acc="global")
+        opts.update(cfg)
+        k.configure((n, n), **opts)
+        return k
     if w.linreg2:
         k.set_args(None, None, host.params(0), host.params(1), d0, d1, None, w.size)
     else:

@@ -177,7 +177,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n, K, Wm = args.n, args.steps, args.warmup
-    wl_kw = {"steps": args.tape_steps} if args.workload == "tape_stress" else {}
+    wl_kw = {"steps": args.tape_steps} if args.workload in ("tape_stress", "matrix_elementwise") else {}
 
     from ad4cl_b200 import workloads as W
     full = W.describe(args.workload, 400 if args.workload == "catch_at_age" else 8, **wl_kw)
