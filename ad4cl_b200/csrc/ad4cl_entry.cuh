@@ -75,19 +75,20 @@ extern __shared__ __align__(16) unsigned char ad4cl_dyn_smem[];
 
 /*
  * Dynamic shared memory layout (doubles unless noted), B = blockDim.x, NW = B/32:
- *   ring      [window][B]
+ *   ring      [window][B]           re-used as the block reduction scratch red[NW][ncols] after the
+ *                                   last work-item (the region is max(window*B, NW*ncols) doubles)
  *   thread_acc[nparams][B]          kAccThread only
  *   warp_acc  [NW][nparams]         kAccWarp only
- *   red       [NW][ncols]           block reduction scratch
  *   tape rows [NW][smem_region]     tape_in_smem only (bytes)
  */
 __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int window, int acc_mode,
         bool tape_in_smem, unsigned cap_slots, bool far) {
     const int nw = block / 32;
+    const size_t red = (size_t) nw * ((acc_mode == kAccGlobal ? 0 : nparams) + 3);
     size_t d = (size_t) window * block;
+    if (d < red) d = red;
     if (acc_mode == kAccThread) d += (size_t) nparams * block;
     if (acc_mode == kAccWarp) d += (size_t) nw * nparams;
-    d += (size_t) nw * ((acc_mode == kAccGlobal ? 0 : nparams) + 3);
     size_t bytes = d * sizeof (double);
     bytes = (bytes + 127) & ~(size_t) 127;
     if (tape_in_smem) bytes += (size_t) nw * warp_region_bytes(cap_slots, far);
@@ -107,10 +108,12 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 
     double* smem = reinterpret_cast<double*> (ad4cl_dyn_smem);
     double* ring = smem;
-    double* thread_acc = ring + (size_t) L.window * B;
+    double* red = smem; /* the ring is dead (all zero) once the last work-item has been swept */
+    size_t shared_region = (size_t) L.window * B;
+    if (shared_region < (size_t) nw * ncols) shared_region = (size_t) nw * ncols;
+    double* thread_acc = ring + shared_region;
     double* warp_acc = thread_acc + (MODE == kAccThread ? (size_t) P * B : 0);
-    double* red = warp_acc + (MODE == kAccWarp ? (size_t) nw * P : 0);
-    size_t dbl_bytes = (size_t) ((red + (size_t) nw * ncols) - smem) * sizeof (double);
+    size_t dbl_bytes = (size_t) ((warp_acc + (MODE == kAccWarp ? (size_t) nw * P : 0)) - smem) * sizeof (double);
     dbl_bytes = (dbl_bytes + 127) & ~(size_t) 127;
 
     for (int i = tid; i < L.window * B; i += B) ring[i] = 0.0;
