@@ -176,7 +176,11 @@ enum AccMode : int {
 /* shared-memory accesses by 32-bit shared-window address: no generic-pointer
    conversion in the sweep's inner loop */
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
-    return (unsigned) __cvta_generic_to_shared(p);
+    /* volatile: the compiler must keep the result in a register instead of re-deriving
+       the shared window base (5 instructions) at every use inside the sweep loop */
+    unsigned a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+    return a;
 }
 __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
