@@ -90,6 +90,10 @@ struct ad_private_gradient_structure {
 
 #define AD4CL_DEV __device__ __forceinline__
 
+/* feature macros kernel sources can test (both are additions over the reference's ad.cl) */
+#define AD4CL_HAVE_PAD_MATH 1
+#define AD4CL_HAVE_COMMIT_P 1
+
 /* ------------------------------------------------------------------ init */
 
 /* ad.cl:129-131 */
@@ -307,6 +311,13 @@ AD4CL_DEV void pad_plus_eq_g(struct ad_gradient_structure* gs, struct ad_variabl
     pad_plus_eq(gs, a, b);
 }
 
+/* Test / debug accessor: the `back`-th most recent slot of the thread tape (0 = last pushed). */
+AD4CL_DEV void ad4cl_tape_peek(const struct ad_gradient_structure* gs, int back, double* dx, int* word) {
+    const char* row = gs->tape->cur - (size_t) (back + 1) * ad4cl::kRowBytes;
+    *dx = *reinterpret_cast<const double*> (row);
+    *word = *reinterpret_cast<const int*> (row + gs->tape->id_off);
+}
+
 /*
  * Sweep of a private stack (the reference declares the structure, ad.cl:91-97,
  * but has no sweep for it).  gradient[] must hold nvars zeros, nvars >
@@ -329,4 +340,33 @@ AD4CL_DEV void ad_gradient_p(const struct ad_private_gradient_structure* gs, con
         }
         gradient[idw & ad4cl::kIdMask] += w * gs->slot_dx[s];
     }
+}
+
+/*
+ * Pre-accumulation: fold a finished private stack into the thread tape.  Sweeps `pgs`
+ * seeded at `out` into a private gradient of PRIVATE_GRADIENT_SIZE adjoints (the macro the
+ * reference declares for exactly this, ad.cl:55-57, and never uses) and records
+ * out = sum_p g_p * theta_p-linearisation as one short chain of operators whose operands
+ * are the independents (ids below gs->current_ad_variable_id).  The private stack lives in
+ * registers / local memory, so only P slots per work-item reach the arena instead of one
+ * slot per operand.  Ids on the private stack must be independents' ids or the private
+ * stack's own results, i.e. pgs->current_ad_variable_id >= gs->current_ad_variable_id, and
+ * every id must be below PRIVATE_GRADIENT_SIZE.
+ */
+AD4CL_DEV struct ad_variable ad_commit_p(struct ad_gradient_structure* gs,
+        const struct ad_private_gradient_structure* pgs, const struct ad_variable out) {
+    struct ad_variable ret = {out.value, 0};
+    if (gs->recording != 1) return ret;
+    double g[PRIVATE_GRADIENT_SIZE];
+    for (int i = 0; i < PRIVATE_GRADIENT_SIZE; i++) g[i] = 0.0;
+    ad_gradient_p(pgs, out, g);
+    const int nparams = gs->current_ad_variable_id;
+    int have = 0;
+    for (int p = 0; p < nparams && p < PRIVATE_GRADIENT_SIZE; p++) {
+        if (g[p] == 0.0) continue;
+        ret.id = have ? ad4cl::record2(gs, 1.0, ret.id, g[p], p) : ad4cl::record1(gs, g[p], p);
+        have = 1;
+    }
+    if (!have) ad_init_var_g(gs, &ret, out.value); /* constant: a leaf with no partials */
+    return ret;
 }

@@ -16,6 +16,7 @@
 
 #include "../kernels/objectives.cl"
 #include "../kernels/matrix.cl"
+#include "../kernels/op_probe.cl"
 
 #define OBJECTIVE_ABI(NAME)                                                                  \
     AD4CL_OBJECTIVE_ENTRY(NAME,                                                               \
@@ -33,6 +34,9 @@ OBJECTIVE_ABI(regression_logistic)
 OBJECTIVE_ABI(catch_at_age)
 OBJECTIVE_ABI(tape_stress)
 OBJECTIVE_ABI(op_zoo)
+OBJECTIVE_ABI(op_zoo_pad)
+OBJECTIVE_ABI(op_zoo_private)
+OBJECTIVE_ABI(op_probe)
 AD4CL_OBJECTIVE_ENTRY(matrix_product,
     (struct ad_variable* A, struct ad_variable* B, int widthA, int widthB),
     (gs, gradient_stack, A, B, out, widthA, widthB))
@@ -50,6 +54,9 @@ extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(catch_at_age, "GSVDDOiii"),
     ROW(tape_stress, "GSVDDOiii"),
     ROW(op_zoo, "GSVDDOiii"),
+    ROW(op_zoo_pad, "GSVDDOiii"),
+    ROW(op_zoo_private, "GSVDDOiii"),
+    ROW(op_probe, "GSVDDOiii"),
     ROW(matrix_product, "GSVVOii"),
     ROW(matrix_elementwise, "GSVVOii"),
     {nullptr, {nullptr, nullptr, nullptr}, nullptr},

@@ -21,6 +21,7 @@ __kernel void matrix_product(__global struct ad_gradient_structure* gs,
     ad_init(gs, gradient_stack);
     const int i = get_global_id(0);
     const int j = get_global_id(1);
+    if (i >= widthB || j >= widthA) return; /* NDRange padded to whole work-groups */
     struct ad_variable value;
     ad_init_var_g(gs, &value, 0.0);
     for (int k = 0; k < widthA; k++) {
@@ -38,6 +39,7 @@ __kernel void matrix_elementwise(__global struct ad_gradient_structure* gs,
     ad_init(gs, gradient_stack);
     const int i = get_global_id(0);
     const int j = get_global_id(1);
+    if (i >= width || j >= width) return;
     const int e = i + width * j;
     struct ad_variable r;
     if (op == 0) r = ad_times(gs, A[e], B[e]);

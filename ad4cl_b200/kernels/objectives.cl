@@ -257,3 +257,104 @@ __kernel void op_zoo(__global struct ad_gradient_structure* gs,
         out[id] = acc;
     }
 }
+
+/* the same chain through the block-reserved family (incl. the pad_ math functions this
+ * runtime adds; with the reference runtime or the port only the arithmetic part exists,
+ * so the oracle compares against op_zoo of the global family: same values, and the same
+ * partials except pad_times_dv, which is correct in the reference, ad.cl:840) */
+#ifdef AD4CL_HAVE_PAD_MATH
+__kernel void op_zoo_pad(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_gradient_structure pgs;
+        ad_init(gs, gradient_stack);
+        pad_init(47, &pgs, gs, gradient_stack);
+        const double x = d0[id];
+        struct ad_variable a = pad_times_vd(&pgs, theta[0], x);
+        struct ad_variable b = pad_plus_vd(&pgs, theta[1], x);
+        struct ad_variable c = pad_plus_dv(&pgs, 0.25, theta[2]);
+        struct ad_variable acc = pad_plus(&pgs, a, b);
+        acc = pad_minus(&pgs, acc, c);
+        acc = pad_minus_vd(&pgs, acc, 0.125);
+        acc = pad_minus_dv(&pgs, 9.0, acc);
+        acc = pad_times(&pgs, acc, b);
+        acc = pad_times_dv(&pgs, 0.75, acc);
+        acc = pad_divide(&pgs, acc, b);
+        acc = pad_divide_vd(&pgs, acc, 1.5);
+        acc = pad_plus(&pgs, acc, pad_divide_dv(&pgs, 2.0, b));
+        pad_plus_eq(&pgs, &acc, a);
+        pad_plus_eq_d(&pgs, &acc, 0.5);
+        acc = pad_plus(&pgs, acc, pad_sin(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_cos(&pgs, b));
+        acc = pad_plus(&pgs, acc, pad_tan(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_asin(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_acos(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_atan(&pgs, b));
+        acc = pad_plus(&pgs, acc, pad_sinh(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_cosh(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_tanh(&pgs, b));
+        acc = pad_plus(&pgs, acc, pad_exp(&pgs, a));
+        acc = pad_plus(&pgs, acc, pad_log(&pgs, b));
+        acc = pad_plus(&pgs, acc, pad_log10(&pgs, b));
+        acc = pad_plus(&pgs, acc, pad_sqrt(&pgs, b));
+        acc = pad_plus(&pgs, acc, pad_pow(&pgs, b, a));
+        acc = pad_plus(&pgs, acc, pad_pow_vd(&pgs, b, 1.75));
+        acc = pad_plus(&pgs, acc, pad_pow_dv(&pgs, 1.5, a));
+        out[id] = acc;
+    }
+}
+#endif
+
+/* the same chain on a PRIVATE stack (ad.cl:1216-1829), pre-accumulated into the thread
+ * tape with ad_commit_p: only 3 slots per work-item leave the registers / local memory */
+#ifdef AD4CL_HAVE_COMMIT_P
+__kernel void op_zoo_private(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __global struct ad_variable* theta,
+        __global double* d0, __global double* d1,
+        __global struct ad_variable* out, int size, int i0, int i1) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_private_gradient_structure p;
+        ad_init_p(&p);
+        p.current_ad_variable_id = gs->current_ad_variable_id; /* private results follow the independents */
+        const double x = d0[id];
+        struct ad_variable a = ad_times_vd_p(&p, theta[0], x);
+        struct ad_variable b = ad_plus_vd_p(&p, theta[1], x);
+        struct ad_variable c = ad_plus_dv_p(&p, 0.25, theta[2]);
+        struct ad_variable acc = ad_plus_p(&p, a, b);
+        acc = ad_minus_p(&p, acc, c);
+        acc = ad_minus_vd_p(&p, acc, 0.125);
+        acc = ad_minus_dv_p(&p, 9.0, acc);
+        acc = ad_times_p(&p, acc, b);
+        acc = ad_times_dv_p(&p, 0.75, acc);
+        acc = ad_divide_p(&p, acc, b);
+        acc = ad_divide_vd_p(&p, acc, 1.5);
+        acc = ad_plus_p(&p, acc, ad_divide_dv_p(&p, 2.0, b));
+        ad_plus_eq_p(&p, &acc, a);
+        ad_plus_eq_d_p(&p, &acc, 0.5);
+        acc = ad_plus_p(&p, acc, ad_sin_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_cos_p(&p, b));
+        acc = ad_plus_p(&p, acc, ad_tan_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_asin_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_acos_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_atan_p(&p, b));
+        acc = ad_plus_p(&p, acc, ad_sinh_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_cosh_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_tanh_p(&p, b));
+        acc = ad_plus_p(&p, acc, ad_exp_p(&p, a));
+        acc = ad_plus_p(&p, acc, ad_log_p(&p, b));
+        acc = ad_plus_p(&p, acc, ad_log10_p(&p, b));
+        acc = ad_plus_p(&p, acc, ad_sqrt_p(&p, b));
+        acc = ad_plus_p(&p, acc, ad_pow_p(&p, b, a));
+        acc = ad_plus_p(&p, acc, ad_pow_vd_p(&p, b, 1.75));
+        acc = ad_plus_p(&p, acc, ad_pow_dv_p(&p, 1.5, a));
+        out[id] = ad_commit_p(gs, &p, acc);
+    }
+}
+#endif
