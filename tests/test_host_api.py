@@ -78,3 +78,22 @@ def test_main_cpp_loop_on_cuda(tmp_path, oracle_api):
         assert abs(f - ref["f"]) <= 1e-9 + 1e-12 * abs(ref["f"])
         assert abs(da - ref["grad"][0]) <= 1e-9 + 1e-12 * abs(ref["grad"][0])
         assert abs(db - ref["grad"][1]) <= 1e-9 + 1e-12 * abs(ref["grad"][1])
+
+
+@pytest.mark.gpu
+def test_optimiser_drives_the_cuda_path():
+    """examples/fit_catch_at_age.py: L-BFGS over ad4cl_cuda_eval recovers the parameters the
+    synthetic catch was generated from (the soft-golden style of the reference's .par files:
+    simple.par a -> 2, b -> 4)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fit", os.path.join(REPO, "examples", "fit_catch_at_age.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from ad4cl_b200 import workloads as W
+    n = 200_000
+    res, truth, evals = mod.fit(n, maxiter=300, verbose=False)
+    start = W.describe("catch_at_age", n).theta
+    assert abs(res.x[93] - truth[93]) < 0.01                                  # log sigma is sharply determined
+    assert np.abs(res.x - truth).max() < np.abs(start - truth).max()          # closer to the generating parameters
+    assert np.abs(res.jac).max() < 1e-3 * n                                   # gradient per observation ~ 0
+    assert evals < 1500
