@@ -476,6 +476,84 @@ int status_to_error(ad4cl_kernel* k, int st) {
 
 } // namespace
 
+/*
+ * One-shot all-reduce of a short fp64 vector over NVLink peer memory (one process per GPU).
+ * Every rank stores its vector into slot [parity][rank] of EVERY rank's inbox (peer stores),
+ * publishes a flag carrying the epoch, waits until all `world` flags of its own inbox show the
+ * epoch, and sums the slots in rank order -- so all ranks obtain bit-identical results, the sum
+ * order does not depend on arrival order, and the latency is one NVLink store + one flag flight
+ * instead of a collective's ring/tree.  Two parities: a rank can run at most one epoch ahead.
+ * The scalar epilogue of the objective is applied to the reduced vector in the same kernel.
+ */
+namespace {
+
+struct CommPeers {
+    double* inbox[16]; /* rank r's inbox as mapped into this process (own inbox at [rank]) */
+};
+
+__global__ void __launch_bounds__(256) oneshot_allreduce(CommPeers peers, int rank, int world, int stride,
+        int n, unsigned long long epoch, double* __restrict__ data, int nparams, int epilogue, double n_obs,
+        int* __restrict__ status) {
+    const int tid = threadIdx.x;
+    const size_t slot_of_me = ((size_t) (epoch & 1) * world + rank) * stride;
+    for (int idx = tid; idx < world * n; idx += 256) {
+        const int r = idx / n, i = idx - r * n;
+        peers.inbox[r][slot_of_me + i] = data[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*> (peers.inbox[tid] + slot_of_me + stride - 1);
+        *flag = epoch;
+    }
+    double* mine = peers.inbox[rank] + (size_t) (epoch & 1) * world * stride;
+    __shared__ int failed;
+    if (tid == 0) failed = 0;
+    __syncthreads();
+    if (tid < world) {
+        const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*> (mine + (size_t) tid * stride + stride - 1);
+        const long long t0 = clock64();
+        while (*flag != epoch) {
+            if (clock64() - t0 > 4000000000LL) { /* ~2 s: a peer never arrived; report instead of hanging */
+                failed = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (failed) {
+        if (tid == 0) atomicOr(status, 4);
+        return;
+    }
+    double S = 0.0;
+    if (epilogue == 1) {
+        for (int r = 0; r < world; r++) S += *reinterpret_cast<const volatile double*> (mine + (size_t) r * stride + nparams);
+    }
+    for (int i = tid; i < n; i += 256) {
+        double v = 0.0;
+        for (int r = 0; r < world; r++) v += *reinterpret_cast<const volatile double*> (mine + (size_t) r * stride + i);
+        if (epilogue == 1) {
+            if (i < nparams) v *= (n_obs / 2.0) * (1.0 / S);
+            else if (i == nparams) v = (n_obs / 2.0) * log(S);
+        }
+        data[i] = v;
+    }
+}
+
+} // namespace
+
+struct ad4cl_comm {
+    ad4cl_context* ctx = nullptr;
+    int rank = 0, world = 1, stride = 0;
+    double* inbox = nullptr;           /* [2][world][stride] */
+    CommPeers peers{};
+    bool connected = false;
+    unsigned long long epoch = 0;
+    int* status_dev = nullptr;
+    int* status_pinned = nullptr;
+};
+
 /* ============================================================ C ABI */
 #pragma GCC visibility push(default)
 extern "C" {
@@ -881,6 +959,88 @@ int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* k, double* mean_ms, long long* 
         k->prof_sum_ms = 0.0;
         k->prof_count = 0;
     }
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_create(ad4cl_context* ctx, int rank, int world, int max_doubles, ad4cl_comm** out) {
+    if (!ctx || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || max_doubles < 1)
+        return fail(AD4CL_ERR_INVALID, "bad communicator shape rank=%d world=%d n=%d (world <= 16)", rank, world, max_doubles);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ad4cl_comm* c = new ad4cl_comm();
+    c->ctx = ctx;
+    c->rank = rank;
+    c->world = world;
+    c->stride = max_doubles + 1; /* + the flag word */
+    const size_t bytes = sizeof (double) * 2 * (size_t) world * c->stride;
+    CUDA_TRY(cudaMalloc(&c->inbox, bytes));
+    CUDA_TRY(cudaMemset(c->inbox, 0, bytes));
+    CUDA_TRY(cudaMalloc(&c->status_dev, sizeof (int)));
+    CUDA_TRY(cudaMemset(c->status_dev, 0, sizeof (int)));
+    CUDA_TRY(cudaMallocHost(&c->status_pinned, sizeof (int)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    c->peers.inbox[rank] = c->inbox;
+    *out = c;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_handle_bytes(void) { return (int) sizeof (cudaIpcMemHandle_t); }
+
+int ad4cl_cuda_comm_handle(ad4cl_comm* c, void* handle_out) {
+    if (!c || !handle_out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->inbox));
+    memcpy(handle_out, &h, sizeof h);
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_connect(ad4cl_comm* c, const void* handles) {
+    if (!c || !handles) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*) handles + (size_t) r * sizeof h, sizeof h);
+        void* p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peers.inbox[r] = (double*) p;
+    }
+    c->connected = true;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_allreduce(ad4cl_comm* c, double* data_dev, int n, int nparams, int epilogue, double n_obs) {
+    if (!c || !data_dev) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (!c->connected && c->world > 1) return fail(AD4CL_ERR_INVALID, "communicator is not connected");
+    if (n < 1 || n > c->stride - 1) return fail(AD4CL_ERR_INVALID, "vector of %d doubles exceeds the communicator's %d", n, c->stride - 1);
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    c->epoch++;
+    oneshot_allreduce<<<1, 256, 0, c->ctx->stream>>>(c->peers, c->rank, c->world, c->stride, n, c->epoch, data_dev,
+            nparams, epilogue, n_obs, c->status_dev);
+    CUDA_TRY(cudaGetLastError());
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_check(ad4cl_comm* c) {
+    if (!c) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(c->status_pinned, c->status_dev, sizeof (int), cudaMemcpyDeviceToHost, c->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->ctx->stream));
+    if (*c->status_pinned) return fail(AD4CL_ERR_CUDA, "one-shot all-reduce timed out waiting for a peer (rank %d of %d)", c->rank, c->world);
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_destroy(ad4cl_comm* c) {
+    if (!c) return AD4CL_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    for (int r = 0; r < c->world; r++)
+        if (r != c->rank && c->peers.inbox[r]) cudaIpcCloseMemHandle(c->peers.inbox[r]);
+    cudaFree(c->inbox);
+    cudaFree(c->status_dev);
+    cudaFreeHost(c->status_pinned);
+    delete c;
     return AD4CL_OK;
 }
 

@@ -38,12 +38,16 @@ def apply_epilogue(raw: torch.Tensor, nparams: int, epilogue: str, n_total: floa
 class ShardedObjective:
     """local_eval(theta, raw_out) must fill raw_out (P+3 doubles, on `device`) with this
     rank's raw sums for parameters `theta` (P doubles on `device`), asynchronously on
-    the current stream."""
+    the current stream.
+
+    `comm` (a connected host.Comm) switches the reduction from torch.distributed's
+    all_reduce (NCCL / gloo) to the library's one-shot NVLink all-reduce, which also applies
+    the epilogue on the device."""
 
     def __init__(self, local_eval: Callable[[torch.Tensor, torch.Tensor], None], nparams: int,
-                 epilogue: str, n_total: int, device: torch.device, group=None):
+                 epilogue: str, n_total: int, device: torch.device, group=None, comm=None):
         self.local_eval, self.P, self.epilogue, self.n_total = local_eval, nparams, epilogue, n_total
-        self.device, self.group = device, group
+        self.device, self.group, self.comm = device, group, comm
         self.raw = torch.zeros(nparams + 3, dtype=torch.float64, device=device)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
@@ -54,13 +58,37 @@ class ShardedObjective:
             dist.all_reduce(self.raw, op=dist.ReduceOp.SUM, group=self.group)
         return self.raw
 
+    def eval_device(self, theta: torch.Tensor) -> torch.Tensor:
+        """-> [grad..., f, ops, slots] on the device, epilogue applied, no host synchronisation."""
+        if self.comm is not None and self.world > 1:
+            self.local_eval(theta, self.raw)
+            self.comm.allreduce(self.raw.data_ptr(), self.P + 3, self.P, self.epilogue, float(self.n_total))
+            return self.raw
+        return apply_epilogue(self.eval_raw(theta), self.P, self.epilogue, float(self.n_total))
+
     def eval(self, theta: torch.Tensor):
         """-> (f, grad) as a python float and a host tensor."""
-        out = apply_epilogue(self.eval_raw(theta), self.P, self.epilogue, float(self.n_total)).cpu()
+        out = self.eval_device(theta).cpu()
         return float(out[self.P]), out[: self.P].clone()
 
 
-def from_kernel(kernel, workload, device: torch.device, group=None) -> ShardedObjective:
+def connect_oneshot(ctx, nparams: int, group=None):
+    """Create the one-shot all-reduce communicator of this rank and connect it to its peers:
+    the IPC handles are exchanged with torch.distributed (plumbing), the data path is the
+    library's own kernel over NVLink peer memory.  Returns None when world size is 1."""
+    from . import host
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = host.Comm(ctx, rank, world, nparams + 3)
+    handles = [None] * world
+    dist.all_gather_object(handles, comm.handle(), group=group)
+    comm.connect(handles)
+    dist.barrier(group)
+    return comm
+
+
+def from_kernel(kernel, workload, device: torch.device, group=None, comm=None) -> ShardedObjective:
     """Wrap a configured host.Kernel bound to this rank's shard of `workload`."""
     P = workload.nparams
 
@@ -68,4 +96,4 @@ def from_kernel(kernel, workload, device: torch.device, group=None) -> ShardedOb
         kernel.eval_device(theta.data_ptr(), P, raw.data_ptr(), want_grad=True, apply_epilogue=False)
 
     n_total = int(workload.epilogue_n) if workload.epilogue_n else workload.size
-    return ShardedObjective(local_eval, P, workload.epilogue, n_total, device, group)
+    return ShardedObjective(local_eval, P, workload.epilogue, n_total, device, group, comm)

@@ -91,6 +91,12 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
     lib.ad4cl_cuda_kernel_profile.argtypes = [c_void_p, c_int]
+    lib.ad4cl_cuda_comm_create.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]
+    lib.ad4cl_cuda_comm_handle.argtypes = [c_void_p, c_void_p]
+    lib.ad4cl_cuda_comm_connect.argtypes = [c_void_p, c_void_p]
+    lib.ad4cl_cuda_comm_allreduce.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double]
+    lib.ad4cl_cuda_comm_check.argtypes = [c_void_p]
+    lib.ad4cl_cuda_comm_destroy.argtypes = [c_void_p]
     lib.ad4cl_cuda_kernel_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_longlong), c_int]
     return lib
 
@@ -248,6 +254,35 @@ class Kernel:
     def free(self) -> None:
         if self._h:
             lib.ad4cl_cuda_kernel_free(self._h)
+            self._h = None
+
+
+class Comm:
+    """One-shot NVLink all-reduce of the short result vector (see include/ad4cl_cuda.h)."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, max_doubles: int):
+        h = c_void_p()
+        _check(lib.ad4cl_cuda_comm_create(ctx._h, rank, world, max_doubles, byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(lib.ad4cl_cuda_comm_handle_bytes())
+        _check(lib.ad4cl_cuda_comm_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles: list[bytes]) -> None:
+        blob = b"".join(handles)
+        _check(lib.ad4cl_cuda_comm_connect(self._h, blob))
+
+    def allreduce(self, data_dev_ptr: int, n: int, nparams: int, epilogue: str = "sum", n_obs: float = 0.0) -> None:
+        _check(lib.ad4cl_cuda_comm_allreduce(self._h, data_dev_ptr, n, nparams, EPILOGUE[epilogue], float(n_obs)))
+
+    def check(self) -> None:
+        _check(lib.ad4cl_cuda_comm_check(self._h))
+
+    def destroy(self) -> None:
+        if self._h:
+            lib.ad4cl_cuda_comm_destroy(self._h)
             self._h = None
 
 

@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--local-size", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
+                    help="N > 1: the library's one-shot NVLink all-reduce (default) or torch.distributed NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -185,7 +187,8 @@ def main():
                           f"{n} observations x {full.nparams} parameters)",
               "n_obs": n, "n_params": full.nparams,
               "parallelism": f"observations sharded contiguously over {args.gpus} GPU(s)"
-                             + (", one NCCL all-reduce of [grad, sum] per evaluation" if args.gpus > 1 else "")}
+                             + (f", one {args.allreduce} all-reduce of [grad, sum, ops, slots] per evaluation"
+                                if args.gpus > 1 else "")}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -236,14 +239,15 @@ def main():
     theta_dev = theta_host.to(dev)
     result_dev = torch.zeros(P + 3, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    sharded = D.from_kernel(k, w, dev) if world > 1 else None
+    comm = D.connect_oneshot(ctx, P) if (world > 1 and args.allreduce == "oneshot") else None
+    sharded = D.from_kernel(k, w, dev, comm=comm) if world > 1 else None
 
     def step_device():
         nonlocal result_dev
         if world == 1:
             k.eval_device(theta_dev.data_ptr(), P, result_dev.data_ptr(), want_grad=True, apply_epilogue=True)
         else:   # local raw sums -> ONE all-reduce of P+3 doubles -> epilogue on every rank
-            result_dev = D.apply_epilogue(sharded.eval_raw(theta_dev), P, w.epilogue, float(n))
+            result_dev = sharded.eval_device(theta_dev)
 
     def barrier():
         if world > 1:
@@ -337,13 +341,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * (P + 3) + 4,
                     "note": "observations device-resident across evaluations as in simple.cpp:206-230; "
                             "theta up / [grad,f,ops,slots]+status down every step"},
-            "gpu_launches": 3 * K, "clocks": clocks, "roofline": roofline,
+            "gpu_launches": (4 if comm is not None else 3) * K, "clocks": clocks, "roofline": roofline,
             "ad_ops_per_s": float(st_result[P + 1]) * value,
             "objective": float(st_result[P])}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, info = cpu_eval_rate(args.workload, n, budget_s=25.0)
         line["cpu_baseline"] = info
+    if comm is not None:
+        comm.check()
+        comm.destroy()
     k.free()
     ctx.close()
     if world > 1:

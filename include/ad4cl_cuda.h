@@ -45,6 +45,7 @@ extern "C" {
 typedef struct ad4cl_context ad4cl_context;
 typedef struct ad4cl_kernel ad4cl_kernel;
 typedef struct ad4cl_buffer ad4cl_buffer;
+typedef struct ad4cl_comm ad4cl_comm;
 
 enum {
     AD4CL_OK = 0,
@@ -189,6 +190,26 @@ int ad4cl_cuda_last_stats(ad4cl_kernel* kernel, ad4cl_eval_stats* stats);
  */
 int ad4cl_cuda_kernel_profile(ad4cl_kernel* kernel, int enable);
 int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* kernel, double* mean_ms, long long* launches, int reset);
+
+/*
+ * Multi-GPU (one process per GPU; no counterpart in the reference, which is single device):
+ * a one-shot all-reduce of the short result vector [grad..., S, ops, slots] over NVLink peer
+ * memory, summed in rank order (bit-identical on every rank), with the scalar epilogue fused.
+ *   create   allocate this rank's inbox (max_doubles per peer)
+ *   handle   cudaIpcMemHandle_t of the inbox (ad4cl_cuda_comm_handle_bytes() bytes); the caller
+ *            exchanges the handles of all ranks with whatever it has (torch.distributed, MPI)
+ *   connect  handles of ALL ranks, in rank order
+ *   allreduce  in place on data_dev (n doubles), asynchronous on the context's stream; with
+ *            epilogue = AD4CL_EPILOGUE_HALF_N_LOG, data[nparams] is S and the epilogue is applied
+ *   check    synchronise and report a peer that never arrived
+ */
+int ad4cl_cuda_comm_create(ad4cl_context* ctx, int rank, int world, int max_doubles, ad4cl_comm** comm);
+int ad4cl_cuda_comm_handle_bytes(void);
+int ad4cl_cuda_comm_handle(ad4cl_comm* comm, void* handle_out);
+int ad4cl_cuda_comm_connect(ad4cl_comm* comm, const void* handles);
+int ad4cl_cuda_comm_allreduce(ad4cl_comm* comm, double* data_dev, int n, int nparams, int epilogue, double n_obs);
+int ad4cl_cuda_comm_check(ad4cl_comm* comm);
+int ad4cl_cuda_comm_destroy(ad4cl_comm* comm);
 
 #ifdef __cplusplus
 }
