@@ -1,0 +1,240 @@
+/*
+ * dense_matrix.cu -- the dense-contraction path for config 2 (test/matrix).
+ *
+ * The objective of test/matrix is L = sum_{j,i} G[j,i] * C[j,i] with C = A*B
+ * (matrix_mul.cpp:39-57, 253-261; G = 1 there).  Recording it operator by operator
+ * (matrixmul.cl:5-28: 2n AD operators per element of C) costs 96 n^3 bytes of tape; its
+ * derivative is two more matrix products,
+ *        dL/dA = G * B^T          dL/dB = A^T * G,
+ * 4 n^3 flop in total.  This file computes C, dL/dA and dL/dB with a hand-written fp64 GEMM
+ * for sm_100a, in two variants selected at run time:
+ *   variant 0  CUDA-core DFMA: 64x64 block tile, 64 threads, 8x8 register tile per thread
+ *   variant 1  fp64 tensor-core DMMA (mma.sync.m8n8k4.f64): 64x64 block tile, 4 warps of 32x32
+ * so that ncu / CUDA events decide which one the library uses (profiles/README.md).
+ * Row-major n x n matrices, n a multiple of 64 (the reference uses 256; the config 1024).
+ */
+#include "../../include/ad4cl_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+/* element (r, c) of op(X) where X is row-major n x n and op is identity or transpose */
+template <bool T>
+__device__ __forceinline__ double at(const double* __restrict__ X, int n, int r, int c) {
+    return T ? X[(size_t) c * n + r] : X[(size_t) r * n + c];
+}
+
+/* Load a BM x BK tile of op(A) (k-major in shared memory: As[k][m]) and a BK x BN tile of op(B)
+   (Bs[k][n]).  64 or 128 threads; the contiguous direction of the global read follows the operand's
+   storage so the loads stay coalesced for both op = N and op = T. */
+template <bool TA, bool TB, int NT>
+__device__ __forceinline__ void load_tiles(const double* __restrict__ A, const double* __restrict__ B, int n,
+        int m0, int n0, int k0, double (*As)[BM], double (*Bs)[BN], int tid) {
+    for (int e = tid; e < BM * BK; e += NT) {
+        int m, k;
+        if (TA) { m = e % BM; k = e / BM; }   /* A^T: storage is contiguous along m */
+        else { k = e % BK; m = e / BK; }      /* A  : contiguous along k */
+        As[k][m] = at<TA>(A, n, m0 + m, k0 + k);
+    }
+    for (int e = tid; e < BK * BN; e += NT) {
+        int k, c;
+        if (TB) { k = e % BK; c = e / BK; }   /* B^T: contiguous along k */
+        else { c = e % BN; k = e / BN; }      /* B  : contiguous along n */
+        Bs[k][c] = at<TB>(B, n, k0 + k, n0 + c);
+    }
+}
+
+/* ---------------------------------------------------------------- variant 0: DFMA */
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(64) dgemm_fma(const double* __restrict__ A, const double* __restrict__ B,
+        double* __restrict__ C, int n, double* __restrict__ block_sums) {
+    __shared__ double As[2][BK][BM];
+    __shared__ double Bs[2][BK][BN];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0;
+
+    load_tiles<TA, TB, 64>(A, B, n, m0, n0, 0, As[0], Bs[0], tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < n; k0 += BK) {
+        if (k0 + BK < n) load_tiles<TA, TB, 64>(A, B, n, m0, n0, k0 + BK, As[buf ^ 1], Bs[buf ^ 1], tid);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            double a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = As[buf][kk][ty * 8 + i];
+#pragma unroll
+            for (int j = 0; j < 8; j++) b[j] = Bs[buf][kk][tx * 8 + j];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    double local = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double* row = C + (size_t) (m0 + ty * 8 + i) * n + n0 + tx * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            row[j] = acc[i][j];
+            local += acc[i][j];
+        }
+    }
+    if (block_sums) { /* fixed-order block sum of this tile of C (the objective is sum C) */
+        __shared__ double red[64];
+        red[tid] = local;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int t = 0; t < 64; t++) s += red[t];
+            block_sums[blockIdx.y * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- variant 1: DMMA */
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+            : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(128) dgemm_mma(const double* __restrict__ A, const double* __restrict__ B,
+        double* __restrict__ C, int n, double* __restrict__ block_sums) {
+    __shared__ double As[2][BK][BM];
+    __shared__ double Bs[2][BK][BN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     /* this warp's 32 x 32 sub-tile */
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int g = lane >> 2, q = lane & 3;                      /* fragment coordinates (PTX m8n8k4 layout) */
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    load_tiles<TA, TB, 128>(A, B, n, m0, n0, 0, As[0], Bs[0], tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < n; k0 += BK) {
+        if (k0 + BK < n) load_tiles<TA, TB, 128>(A, B, n, m0, n0, k0 + BK, As[buf ^ 1], Bs[buf ^ 1], tid);
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[buf][k4 + q][wm + i * 8 + g];   /* A[row g][col q] */
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[buf][k4 + q][wn + j * 8 + g];   /* B[row q][col g] */
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    double local = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {       /* C fragment: row g, columns 2q and 2q+1 */
+            double* p = C + (size_t) (m0 + wm + i * 8 + g) * n + n0 + wn + j * 8 + 2 * q;
+            p[0] = acc[i][j][0];
+            p[1] = acc[i][j][1];
+            local += acc[i][j][0] + acc[i][j][1];
+        }
+    if (block_sums) {
+        __shared__ double red[128];
+        red[tid] = local;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int t = 0; t < 128; t++) s += red[t];
+            block_sums[blockIdx.y * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+__global__ void fill_ones(double* p, size_t n) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 1.0;
+}
+
+__global__ void sum_fixed_order(const double* __restrict__ v, int n, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += v[i];
+        *out = s;
+    }
+}
+
+template <bool TA, bool TB>
+cudaError_t gemm(int variant, const double* A, const double* B, double* C, int n, double* block_sums, cudaStream_t st) {
+    dim3 grid(n / BN, n / BM);
+    if (variant == 1) dgemm_mma<TA, TB><<<grid, 128, 0, st>>>(A, B, C, n, block_sums);
+    else dgemm_fma<TA, TB><<<grid, 64, 0, st>>>(A, B, C, n, block_sums);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+extern "C" {
+
+void* ad4cl_cuda_stream(ad4cl_context* ctx);
+const char* ad4cl_cuda_last_error(void);
+int ad4cl_cuda_set_error_(int code, const char* msg); /* shim.cu */
+
+#pragma GCC visibility push(default)
+/*
+ * C = A*B, sum C, dA = G*B^T, dB = A^T*G on device memory (row-major n x n doubles).
+ * G_dev may be NULL (G = 1: the reference's objective sum C); C_dev, dA_dev, dB_dev and sum_dev
+ * may each be NULL to skip that output; workspace_dev: n*n + (n/64)^2 doubles of scratch.
+ * variant 0: DFMA, 1: DMMA.  Asynchronous on the context's stream.
+ */
+int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, const double* A_dev, const double* B_dev,
+        const double* G_dev, double* C_dev, double* dA_dev, double* dB_dev, double* sum_dev, double* workspace_dev) {
+    if (!ctx || !A_dev || !B_dev || !workspace_dev) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "NULL argument");
+    if (n <= 0 || n % 64 != 0) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "dense path needs n to be a multiple of 64");
+    if (variant != 0 && variant != 1) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "variant must be 0 (DFMA) or 1 (DMMA)");
+    cudaStream_t st = (cudaStream_t) ad4cl_cuda_stream(ctx);
+    const size_t nn = (size_t) n * n;
+    double* scratch = workspace_dev;          /* C when the caller does not want it, or G = 1 */
+    double* sums = workspace_dev + nn;
+    const int nblocks = (n / 64) * (n / 64);
+    cudaError_t e = cudaSuccess;
+    if (C_dev || sum_dev) {
+        double* Cout = C_dev ? C_dev : scratch;
+        e = gemm<false, false>(variant, A_dev, B_dev, Cout, n, sum_dev ? sums : nullptr, st);
+        if (e == cudaSuccess && sum_dev) sum_fixed_order<<<1, 32, 0, st>>>(sums, nblocks, sum_dev);
+    }
+    const double* G = G_dev;
+    if (e == cudaSuccess && !G && (dA_dev || dB_dev)) {
+        fill_ones<<<(unsigned) ((nn + 255) / 256), 256, 0, st>>>(scratch, nn);
+        G = scratch;
+    }
+    if (e == cudaSuccess && dA_dev) e = gemm<false, true>(variant, G, B_dev, dA_dev, n, nullptr, st);
+    if (e == cudaSuccess && dB_dev) e = gemm<true, false>(variant, A_dev, G, dB_dev, n, nullptr, st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "dense matrix product failed: %s", cudaGetErrorString(e));
+        return ad4cl_cuda_set_error_(AD4CL_ERR_CUDA, msg);
+    }
+    return AD4CL_OK;
+}
+#pragma GCC visibility pop
+
+} // extern "C"

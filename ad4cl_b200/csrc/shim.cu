@@ -560,6 +560,9 @@ extern "C" {
 
 const char* ad4cl_cuda_last_error(void) { return g_last_error.c_str(); }
 
+/* for the library's other translation units (dense_matrix.cu): set the last-error text */
+int ad4cl_cuda_set_error_(int code, const char* msg) { return fail(code, "%s", msg); }
+
 const char* ad4cl_cuda_device_abi(void) { return ad4cl_embedded_header_hash; }
 
 int ad4cl_cuda_init(int device, ad4cl_context** out) {

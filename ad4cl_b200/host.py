@@ -91,6 +91,7 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
     lib.ad4cl_cuda_kernel_profile.argtypes = [c_void_p, c_int]
+    lib.ad4cl_cuda_matrix_product_dense.argtypes = [c_void_p, c_int, c_int] + [c_void_p] * 8
     lib.ad4cl_cuda_comm_create.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]
     lib.ad4cl_cuda_comm_handle.argtypes = [c_void_p, c_void_p]
     lib.ad4cl_cuda_comm_connect.argtypes = [c_void_p, c_void_p]
@@ -337,6 +338,20 @@ class Context:
         _check(lib.ad4cl_cuda_kernel_from_cubin(self._h, cubin, len(cubin), entry.encode(), signature.encode(),
                                                 1 if quirks else 0, byref(h)))
         return Kernel(self, h, entry)
+
+    def matrix_product_dense(self, n: int, A: Buffer, B: Buffer, *, G: Buffer | None = None, C: Buffer | None = None,
+                             dA: Buffer | None = None, dB: Buffer | None = None, total: Buffer | None = None,
+                             workspace: Buffer | None = None, variant: int = 0) -> None:
+        """config 2 without a tape: C = A B, sum C, dL/dA = G B^T, dL/dB = A^T G (asynchronous)."""
+        p = lambda b: None if b is None else b.device_ptr  # noqa: E731
+        _check(lib.ad4cl_cuda_matrix_product_dense(self._h, variant, n, p(A), p(B), p(G), p(C), p(dA), p(dB),
+                                                   p(total), p(workspace)))
+
+    def synchronize(self) -> None:
+        """Wait for everything queued on the context's stream (a 0-byte blocking download)."""
+        if not hasattr(self, "_sync_buf"):
+            self._sync_buf = self.buffer(nbytes=8)
+        self._sync_buf.download(np.uint8, 0)
 
     def close(self) -> None:
         if self._h:

@@ -284,6 +284,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = K / (total_ms * 1e-3)
+    kernel_ms_by_rank = [kernel_ms]
+    if world > 1:   # how well the shards are balanced: every rank's mean fused-kernel time
+        tk = torch.zeros(world, dtype=torch.float64, device=dev)
+        tk[rank] = kernel_ms
+        dist.all_reduce(tk)
+        kernel_ms_by_rank = [round(v, 4) for v in tk.tolist()]
 
     # ---- e2e: host theta -> host result every step (wall clock around the API call)
     e2e_times = []
@@ -326,7 +332,7 @@ def main():
     stats = k.stats()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": f"{w.kernel}__entry (fused record+sweep+block reduce)",
-                "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_launches,
+                "kernel_ms": kernel_ms, "kernel_ms_by_rank": kernel_ms_by_rank, "kernel_launches_timed": kernel_launches,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = 24 B x operand slots + inputs + 8(P+1) (SURVEY 8d); the arena of "
                         "resident warps can stay L2 resident for short tapes, so frac may exceed 1 (see traffic)"}

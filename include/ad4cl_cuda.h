@@ -192,6 +192,19 @@ int ad4cl_cuda_kernel_profile(ad4cl_kernel* kernel, int enable);
 int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* kernel, double* mean_ms, long long* launches, int reset);
 
 /*
+ * Dense-contraction path for test/matrix (matrix_mul.cpp:39-57, matrixmul.cl:5-28): instead of
+ * recording 2n AD operators per element of C = A*B, compute C, sum C and the derivative of
+ * L = sum_{j,i} G[j,i] C[j,i] as two more products, dL/dA = G*B^T and dL/dB = A^T*G.
+ * Row-major n x n doubles in device memory, n a multiple of 64.  G_dev NULL means G = 1 (the
+ * reference's objective).  C_dev, dA_dev, dB_dev, sum_dev may each be NULL to skip that output.
+ * workspace_dev: n*n + (n/64)^2 doubles.  variant 0: CUDA-core DFMA, 1: fp64 tensor-core DMMA.
+ * Asynchronous on the context's stream.
+ */
+int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, const double* A_dev,
+        const double* B_dev, const double* G_dev, double* C_dev, double* dA_dev, double* dB_dev,
+        double* sum_dev, double* workspace_dev);
+
+/*
  * Multi-GPU (one process per GPU; no counterpart in the reference, which is single device):
  * a one-shot all-reduce of the short result vector [grad..., S, ops, slots] over NVLink peer
  * memory, summed in rank order (bit-identical on every rank), with the scalar epilogue fused.

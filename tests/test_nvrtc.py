@@ -130,6 +130,18 @@ def test_reference_matrixmul_cl_runs_on_the_cuda_runtime(ctx, oracle_api):
 
 
 @pytest.mark.gpu
+def test_reference_tiled_matrixmul_runs_on_the_cuda_runtime(ctx, oracle_api):
+    """matrixmul.cl:63-172: __local 16x16 tiles, get_group_id/get_local_id, two work-group barriers
+    per tile -- a CTA is one OpenCL work-group, barrier() is __syncthreads()."""
+    from ad4cl_b200 import host
+    path = os.path.join(CUBINS, f"ref_matrixmul_tiled_cl.q.{host.device_abi()}.cubin")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/ref_matrixmul_tiled_cl.q.*.cubin not built")
+    k = ctx.from_cubin(open(path, "rb").read(), "matrixMult", "GSVVOii", quirks=True)
+    _matrix_case(ctx, oracle_api, k, 48, True, "global")
+
+
+@pytest.mark.gpu
 def test_matrix_golden_256(ctx):
     """The reference's golden file test/matrix/host.txt: sum of the printed C vs our sum C
     (6 printed digits per element), and the tape length on its last line."""
