@@ -239,7 +239,13 @@ def main():
     theta_dev = theta_host.to(dev)
     result_dev = torch.zeros(P + 3, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    comm = D.connect_oneshot(ctx, P) if (world > 1 and args.allreduce == "oneshot") else None
+    comm = None
+    if world > 1 and args.allreduce == "oneshot":
+        try:
+            comm = D.connect_oneshot(ctx, P)
+        except Exception as e:  # noqa: BLE001  (no peer access between these GPUs: NCCL still works)
+            print(f"bench: one-shot all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            args.allreduce = "nccl"
     sharded = D.from_kernel(k, w, dev, comm=comm) if world > 1 else None
 
     def step_device():
