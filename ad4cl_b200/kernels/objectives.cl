@@ -100,16 +100,18 @@ __kernel void regression_logistic(__global struct ad_gradient_structure* gs,
 
 /* ------------------------------------------------------------------------
  * config 4: catch-at-age negative log-likelihood term, P = 100.
- *   work-item i = rep + R*(year + CAA_YEARS*age), R = i0 replicates, so the
- *   replicate index is fastest and (year, age) -- hence the whole op sequence
- *   and every parameter id except the fleet deviation -- is uniform across
- *   neighbouring work-items.
+ *   work-item i = rep_local + R*(year + CAA_YEARS*age), R = i0 replicates of every
+ *   (year, age) cell held by this shard, so the replicate index is fastest and
+ *   (year, age) -- hence the whole op sequence and every parameter id except the
+ *   fleet deviation -- is uniform across neighbouring work-items.
  *   theta: [0,49) log recruitment of cohort c = year - age + 9
  *          [49,89) log F_year   89: a50   90: slope   91: log M
  *          92: log q   93: log sigma   [94,100) fleet deviations of log q
  *   d0   : observed log catch (this shard's observations)
- *   i1   : global index of this shard's first observation (0 on one GPU)
- *   fleet of a replicate = rep*6/R  (6 contiguous blocks of replicates)
+ *   i1   : global index of this shard's first replicate (0 on one GPU): a multi-GPU
+ *          run gives every rank a slice of the replicates of EVERY cell, so all
+ *          shards have the same mix of tape lengths
+ *   fleet of a replicate = (rep / 32) % 6  (fleets cycle over blocks of 32 replicates)
  * Baranov: Z = M + F_y s_a ; N = R_c exp(-sum_{k<a} Z_{y-a+k,k}) ;
  *          Chat = F s / Z (1 - exp(-Z)) N q ;
  *          out = (ln C - ln Chat)^2 / (2 sigma^2) + ln sigma
@@ -124,6 +126,7 @@ __kernel void regression_logistic(__global struct ad_gradient_structure* gs,
 #define CAA_LOGSIGMA 93
 #define CAA_FLEETDEV 94
 #define CAA_FLEETS 6
+#define CAA_FLEET_BLOCK 32
 
 __kernel void catch_at_age(__global struct ad_gradient_structure* gs,
         __global struct ad_entry* gradient_stack,
@@ -134,12 +137,12 @@ __kernel void catch_at_age(__global struct ad_gradient_structure* gs,
     const int id = get_global_id(0);
     if (id < size) {
         const int R = i0;
-        const int rep = (id + i1) % R;
-        const int cell = (id + i1) / R;
+        const int rep = i1 + id % R;
+        const int cell = id / R;
         const int year = cell % CAA_YEARS;
         const int age = cell / CAA_YEARS;
         const int cohort = year - age + (CAA_AGES - 1);
-        const int fleet = (int) (((long long) rep * CAA_FLEETS) / R);
+        const int fleet = (rep / CAA_FLEET_BLOCK) % CAA_FLEETS;
 
         struct ad_variable M = ad_exp(gs, theta[CAA_LOGM]);
         struct ad_variable Z = M;

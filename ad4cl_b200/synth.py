@@ -29,19 +29,27 @@ def splitmix64(counter: np.ndarray) -> np.ndarray:
         return z ^ (z >> np.uint64(31))
 
 
-def uniform(seed: int, start: int, count: int) -> np.ndarray:
-    """U[0,1) doubles for counters start .. start+count-1 of stream `seed`."""
-    idx = np.arange(start, start + count, dtype=np.uint64)
+def uniform_at(seed: int, idx: np.ndarray) -> np.ndarray:
+    """U[0,1) doubles for the counters `idx` (any order, any subset) of stream `seed`."""
     with np.errstate(over="ignore"):
-        ctr = (np.uint64(seed) << np.uint64(40)) + idx
+        ctr = (np.uint64(seed) << np.uint64(40)) + idx.astype(np.uint64)
     return (splitmix64(ctr) >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
 
 
-def normal(seed: int, start: int, count: int) -> np.ndarray:
-    """N(0,1) doubles by Box-Muller from streams 2*seed+1000 and 2*seed+1001."""
-    u1 = uniform(2 * seed + 1000, start, count)
-    u2 = uniform(2 * seed + 1001, start, count)
+def normal_at(seed: int, idx: np.ndarray) -> np.ndarray:
+    """N(0,1) doubles by Box-Muller from streams 2*seed+1000 and 2*seed+1001 at counters `idx`."""
+    u1 = uniform_at(2 * seed + 1000, idx)
+    u2 = uniform_at(2 * seed + 1001, idx)
     return np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def uniform(seed: int, start: int, count: int) -> np.ndarray:
+    """U[0,1) doubles for counters start .. start+count-1 of stream `seed`."""
+    return uniform_at(seed, np.arange(start, start + count, dtype=np.uint64))
+
+
+def normal(seed: int, start: int, count: int) -> np.ndarray:
+    return normal_at(seed, np.arange(start, start + count, dtype=np.uint64))
 
 
 # --------------------------------------------------------------------------- config 1
@@ -87,7 +95,9 @@ def regression(n: int, p: int = 10, kind: str = "linear", start: int = 0, count:
     for j in range(1, p):
         X[j] = uniform(3 * 64 + j, start, count)
     beta = np.array([(-1.0) ** j * (j + 1) / 10.0 for j in range(p)])
-    eta = beta @ X
+    eta = np.zeros(count)
+    for j in range(p):            # fixed order, elementwise: a shard gets the same bits as the whole
+        eta += beta[j] * X[j]
     if kind == "linear":
         y = eta + 0.5 * normal(3, start, count)
     else:
@@ -137,22 +147,26 @@ def caa_log_chat_table(theta: np.ndarray) -> np.ndarray:
     return tab
 
 
-def catch_at_age(n: int, start: int = 0, count: int | None = None):
-    """Observed log catch for work-items start..start+count-1 of an n-observation
-    problem (n must be a multiple of 400): i = rep + R*(year + 40*age), R = n/400.
-    obs = ln Chat(theta*) + 0.3 N(0,1) seed 4; evaluation point theta* + 0.02 N(0,1) seed 5."""
+CAA_FLEET_BLOCK = 32   # fleets cycle over blocks of 32 replicates: fleet = (rep // 32) % 6
+
+
+def catch_at_age(n: int, rep0: int = 0, nrep: int | None = None):
+    """Observed log catch for the replicate slice [rep0, rep0 + nrep) of an n-observation problem
+    (n = 400 R): observation (cell, rep) with cell = year + 40 age has the global index
+    rep + R cell and sits at rep - rep0 + nrep * cell in the returned array (replicate fastest, so the
+    operator sequence is uniform across neighbouring work-items).  obs = ln Chat(theta*) + 0.3 N(0,1)
+    seed 4; evaluation point theta* + 0.02 N(0,1) seed 5.  Returns (obs, theta0, R)."""
     assert n % (CAA_YEARS * CAA_AGES) == 0, "catch-at-age needs n = 400 * replicates"
-    count = n - start if count is None else count
     R = n // (CAA_YEARS * CAA_AGES)
+    nrep = R - rep0 if nrep is None else nrep
     th_true = caa_theta_true()
     tab = caa_log_chat_table(th_true)
-    i = np.arange(start, start + count, dtype=np.int64)
-    rep = i % R
-    cell = i // R
+    cell = np.repeat(np.arange(CAA_YEARS * CAA_AGES, dtype=np.int64), nrep)
+    rep = rep0 + np.tile(np.arange(nrep, dtype=np.int64), CAA_YEARS * CAA_AGES)
     year = cell % CAA_YEARS
     age = cell // CAA_YEARS
-    fleet = (rep * CAA_FLEETS) // R
-    obs = tab[fleet, age, year] + 0.3 * normal(4, start, count)
+    fleet = (rep // CAA_FLEET_BLOCK) % CAA_FLEETS
+    obs = tab[fleet, age, year] + 0.3 * normal_at(4, rep + R * cell)
     theta0 = th_true + 0.02 * normal(5, 0, CAA_P)
     return obs, theta0, R
 

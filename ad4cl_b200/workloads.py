@@ -51,35 +51,8 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     return start, base + (1 if rank < rem else 0)
 
 
-def balanced_range(weights_per_block: list[int], block: int, n: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous shard of rank `rank` whose WORK (not observation count) is 1/world of
-    the total: observation i costs weights_per_block[i // block].  Boundaries are at
-    observation granularity, so shards stay contiguous and the sum over ranks is exact."""
-    total = sum(wt * block for wt in weights_per_block)
-
-    def boundary(r: int) -> int:
-        if r <= 0:
-            return 0
-        if r >= world:
-            return n
-        target = total * r // world
-        acc = 0
-        for b, wt in enumerate(weights_per_block):
-            if acc + wt * block >= target:
-                return min(n, b * block + (target - acc) // wt)
-            acc += wt * block
-        return n
-
-    lo, hi = boundary(rank), boundary(rank + 1)
-    return lo, hi - lo
-
-
 def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 33, p: int = 10) -> Workload:
     start, count = shard_range(n, rank, world)
-    if name == "catch_at_age" and world > 1:
-        # tape length varies 4x with age: split by recorded slots, not by observation count
-        R = n // (synth.CAA_YEARS * synth.CAA_AGES)
-        start, count = balanced_range([sl for _, sl in _caa_per_cell()], R, n, rank, world)
     if name in ("linreg2_main", "linreg2_simple"):
         gen = synth.main_cpp_recipe if name == "linreg2_main" else synth.simple_cpp_recipe
         x, y, (a, b) = gen(n, start, count)
@@ -96,10 +69,14 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
                         max_ops=ops, max_slots=slots, ops_total=ops * count, slots_total=slots * count,
                         input_bytes=8 * (p + 1) * count)
     if name == "catch_at_age":
-        obs, theta0, R = synth.catch_at_age(n, start, count)
-        ops, slots = caa_totals(n, start, count)
-        return Workload(name, name, theta0, obs, None, count, i0=R, i1=start, max_ops=128, max_slots=176,
-                        ops_total=ops, slots_total=slots, input_bytes=8 * count)
+        # tape length varies 4x with age: every rank takes a slice of the REPLICATES of every
+        # (year, age) cell, so all shards have the same mix (a contiguous observation range would not)
+        R = n // (synth.CAA_YEARS * synth.CAA_AGES)
+        rep0, nrep = shard_range(R, rank, world)
+        obs, theta0, _ = synth.catch_at_age(n, rep0, nrep)
+        ops, slots = caa_totals(nrep)
+        return Workload(name, name, theta0, obs, None, len(obs), i0=nrep, i1=rep0, max_ops=128, max_slots=176,
+                        ops_total=ops, slots_total=slots, input_bytes=8 * len(obs))
     if name == "tape_stress":
         x, theta = synth.tape_stress(n, start, count)
         theta = np.ones(p)
@@ -125,18 +102,10 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
     raise KeyError(name)
 
 
-def caa_totals(n: int, start: int, count: int) -> tuple[int, int]:
-    """AD operators and operand slots of catch_at_age over observations [start, start+count)."""
-    R = n // (synth.CAA_YEARS * synth.CAA_AGES)
+def caa_totals(nrep: int) -> tuple[int, int]:
+    """AD operators and operand slots of catch_at_age over `nrep` replicates of every cell."""
     per_cell = _caa_per_cell()
-    ops = slots = 0
-    first_cell, last_cell = start // R, (start + count - 1) // R
-    for cell in range(first_cell, last_cell + 1):
-        lo, hi = max(start, cell * R), min(start + count, (cell + 1) * R)
-        o, s = per_cell[cell]
-        ops += o * (hi - lo)
-        slots += s * (hi - lo)
-    return ops, slots
+    return nrep * sum(o for o, _ in per_cell), nrep * sum(sl for _, sl in per_cell)
 
 
 _CAA_CACHE: list | None = None

@@ -81,18 +81,23 @@ int main(void) { printf("%zu %zu %zu %zu\n", sizeof(ad4cl_kernel_config), sizeof
 
 
 def test_workload_bookkeeping():
-    from ad4cl_b200 import workloads as W
-    w = W.describe("catch_at_age", 8000)
-    parts = [W.describe("catch_at_age", 8000, rank=r, world=3) for r in range(3)]
-    assert sum(p.size for p in parts) == 8000
+    from ad4cl_b200 import synth, workloads as W
+    n = 8000
+    w = W.describe("catch_at_age", n)
+    parts = [W.describe("catch_at_age", n, rank=r, world=3) for r in range(3)]
+    assert sum(p.size for p in parts) == n
     assert sum(p.ops_total for p in parts) == w.ops_total
     assert sum(p.slots_total for p in parts) == w.slots_total
-    assert np.array_equal(np.concatenate([p.d0 for p in parts]), w.d0)      # counter-based generators shard exactly
     assert all(np.array_equal(p.theta, w.theta) for p in parts)
-    assert parts[0].i1 == 0 and all(parts[i].i1 + parts[i].size == parts[i + 1].i1 for i in range(2))
-    work = [p.slots_total for p in parts]
-    assert max(work) - min(work) <= 200 * 3      # balanced by recorded slots to within a few observations
-    assert w.algorithmic_bytes() == 24 * w.slots_total + 8 * 8000 + 8 * 101
+    # replicate slices of every (year, age) cell: shards are balanced to within one replicate per cell
+    R = n // 400
+    assert [p.i1 for p in parts] == [0, 7, 14] and [p.i0 for p in parts] == [7, 7, 6] and R == 20
+    full = w.d0.reshape(400, R)
+    for p in parts:       # counter-based generators shard exactly
+        assert np.array_equal(p.d0.reshape(400, p.i0), full[:, p.i1:p.i1 + p.i0])
+    assert w.algorithmic_bytes() == 24 * w.slots_total + 8 * n + 8 * 101
+    parts = [W.describe("regression_linear", 1000, rank=r, world=3) for r in range(3)]
+    assert np.array_equal(np.concatenate([p.d1 for p in parts]), W.describe("regression_linear", 1000).d1)
     for n, world in ((10, 3), (7, 8), (1000, 8)):
         rs = [W.shard_range(n, r, world) for r in range(world)]
         assert rs[0][0] == 0 and sum(c for _, c in rs) == n

@@ -51,7 +51,7 @@ def _worker(rank, world, port, name, n, out_q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,n,world", [("regression_linear", 3001, 2), ("catch_at_age", 4000, 2),
+@pytest.mark.parametrize("name,n,world", [("regression_linear", 3001, 2), ("catch_at_age", 40000, 2),
                                           ("regression_logistic", 1000, 3)])
 def test_sharded_evaluation_matches_single_process(oracle_api, name, n, world):
     from ad4cl_b200 import workloads as W

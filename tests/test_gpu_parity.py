@@ -33,7 +33,7 @@ CASES = [
     ("linreg2_simple", 5003, {}),
     ("regression_linear", 3001, {}),
     ("regression_logistic", 3001, {}),
-    ("catch_at_age", 8000, {}),
+    ("catch_at_age", 80000, {}),
     ("tape_stress", 777, {"steps": 33}),
     ("tape_stress", 777, {"steps": 200}),
     ("op_zoo", 513, {}),
@@ -79,7 +79,7 @@ def test_accumulator_modes_and_tape_tiers_agree(ctx, oracle_api, acc, tape):
 def test_far_operands(ctx, oracle_api, window, far):
     """catch_at_age re-uses M = exp(log M) up to ~160 operand slots later: with a small
     ring those operands go through the far-adjoint plane."""
-    w = W.describe("catch_at_age", 4000)
+    w = W.describe("catch_at_age", 40000)
     ref, _ = oracle_eval(oracle_api, w, False)
     k = W.bind(ctx, w, window=window, far_plane=far, local_size=64 if window > 64 else None)
     try:
