@@ -16,7 +16,8 @@
  */
 extern "C" __global__ void __launch_bounds__(256) ad4cl_reduce_partials(
         const double* __restrict__ partials, int nblocks, int ncols, int ngrad, int first_col,
-        int epilogue, double n_obs, double* __restrict__ result) {
+        int epilogue, double n_obs, double* __restrict__ result,
+        const int* __restrict__ status = nullptr, double* __restrict__ status_out = nullptr) {
     __shared__ double scratch[2][8];
     const int c = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -43,6 +44,8 @@ extern "C" __global__ void __launch_bounds__(256) ad4cl_reduce_partials(
             else if (c == ngrad) tv = (n_obs / 2.0) * log(ts);
         }
         result[first_col + c] = tv;
+        /* the host path reads the sticky error bits with the result in one copy */
+        if (c == 0 && status_out != nullptr) *status_out = (double) *status;
     }
 }
 

@@ -193,8 +193,12 @@ struct ad4cl_kernel {
     int* status_dev = nullptr;
     char* arena = nullptr;
     double* theta_pinned = nullptr;
-    double* result_pinned = nullptr;
+    struct ad_variable* params_pinned = nullptr; /* host-packed {theta_i, id = i}: no pack kernel on the host path */
+    double* result_pinned = nullptr;             /* nparams + 4 doubles: [grad, f, ops, slots, status] */
     int* status_pinned = nullptr;
+    /* the host evaluation path replayed as one CUDA graph: [0] objective only, [1] with gradient */
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    bool graph_disabled = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ad4cl_eval_stats stats{};
     /* opt-in timing of the fused kernel alone (ad4cl_cuda_kernel_profile) */
@@ -204,10 +208,20 @@ struct ad4cl_kernel {
     double prof_sum_ms = 0.0;
     long long prof_count = 0;
 
+    void drop_graphs() {
+        for (auto& g : graph) {
+            if (g) cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+    }
+
     void release() {
         cudaFree(params_dev); cudaFree(theta_dev); cudaFree(partials); cudaFree(result_dev);
         cudaFree(global_grad); cudaFree(status_dev); cudaFree(arena);
         cudaFreeHost(theta_pinned); cudaFreeHost(result_pinned); cudaFreeHost(status_pinned);
+        cudaFreeHost(params_pinned);
+        params_pinned = nullptr;
+        drop_graphs();
         params_dev = nullptr; theta_dev = nullptr; partials = nullptr; result_dev = nullptr;
         global_grad = nullptr; status_dev = nullptr; arena = nullptr;
         theta_pinned = nullptr; result_pinned = nullptr; status_pinned = nullptr;
@@ -317,7 +331,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     CUDA_TRY(cudaMalloc(&k->params_dev, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
     CUDA_TRY(cudaMalloc(&k->theta_dev, sizeof (double) * (size_t) std::max(nparams, 1)));
     CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) grid * pcols));
-    CUDA_TRY(cudaMalloc(&k->result_dev, sizeof (double) * (size_t) ncols));
+    CUDA_TRY(cudaMalloc(&k->result_dev, sizeof (double) * (size_t) (ncols + 1)));
     CUDA_TRY(cudaMalloc(&k->status_dev, sizeof (int)));
     CUDA_TRY(cudaMemset(k->status_dev, 0, sizeof (int)));
     if (acc == AD4CL_ACC_GLOBAL) CUDA_TRY(cudaMalloc(&k->global_grad, sizeof (double) * (size_t) std::max(nparams, 1)));
@@ -331,7 +345,9 @@ int prepare(ad4cl_kernel* k, int nparams) {
         CUDA_TRY(cudaMemset(k->arena, 0, arena_bytes)); /* far bitmaps must start clear */
     }
     CUDA_TRY(cudaMallocHost(&k->theta_pinned, sizeof (double) * (size_t) std::max(nparams, 1)));
-    CUDA_TRY(cudaMallocHost(&k->result_pinned, sizeof (double) * (size_t) ncols));
+    CUDA_TRY(cudaMallocHost(&k->result_pinned, sizeof (double) * (size_t) (ncols + 1)));
+    CUDA_TRY(cudaMallocHost(&k->params_pinned, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
+    memset(k->params_pinned, 0, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1));
     CUDA_TRY(cudaMallocHost(&k->status_pinned, sizeof (int)));
     if (!k->ev0) CUDA_TRY(cudaEventCreate(&k->ev0));
     if (!k->ev1) CUDA_TRY(cudaEventCreate(&k->ev1));
@@ -384,10 +400,11 @@ int drain_profile(ad4cl_kernel* k) {
 }
 
 /* enqueue pack + fused kernel + second stage on the context's stream */
-int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue) {
+int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue,
+        double* status_out = nullptr) {
     cudaStream_t st = k->ctx->stream;
     const int P = k->nparams;
-    if (P > 0) {
+    if (P > 0 && theta_dev != nullptr) { /* nullptr: params_dev was filled by the caller (host path) */
         pack_params<<<(P + 127) / 128, 128, 0, st>>>(theta_dev, k->params_dev, P);
     }
     ad4cl::LaunchInfo L = k->L;
@@ -450,12 +467,14 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
     const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
     const int epi = apply_epilogue ? k->cfg.epilogue : 0;
     if (k->global_grad) {
-        ad4cl_reduce_partials<<<3, 256, 0, st>>>(k->partials, k->grid, 3, 0, P, epi, n_obs, result_dev);
+        ad4cl_reduce_partials<<<3, 256, 0, st>>>(k->partials, k->grid, 3, 0, P, epi, n_obs, result_dev,
+                k->status_dev, status_out);
         if (P > 0)
             ad4cl_finish_global_grad<<<(P + 255) / 256, 256, 0, st>>>(k->global_grad, P, k->partials, k->grid,
                     epi, n_obs, result_dev);
     } else {
-        ad4cl_reduce_partials<<<P + 3, 256, 0, st>>>(k->partials, k->grid, P + 3, P, 0, epi, n_obs, result_dev);
+        ad4cl_reduce_partials<<<P + 3, 256, 0, st>>>(k->partials, k->grid, P + 3, P, 0, epi, n_obs, result_dev,
+                k->status_dev, status_out);
     }
     CUDA_TRY(cudaGetLastError());
     return AD4CL_OK;
@@ -834,6 +853,7 @@ int ad4cl_cuda_kernel_set_arg_buffer(ad4cl_kernel* k, int index, ad4cl_buffer* b
     a->buf = buf;
     a->first_id = -1;
     a->set = buf != nullptr || a->kind != 'V';
+    k->drop_graphs();
     return AD4CL_OK;
 }
 
@@ -843,6 +863,7 @@ int ad4cl_cuda_kernel_set_arg_int(ad4cl_kernel* k, int index, int value) {
     if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
     a->ival = value;
     a->set = true;
+    k->drop_graphs();
     return AD4CL_OK;
 }
 
@@ -852,6 +873,7 @@ int ad4cl_cuda_kernel_set_arg_double(ad4cl_kernel* k, int index, double value) {
     if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
     a->dval = value;
     a->set = true;
+    k->drop_graphs();
     return AD4CL_OK;
 }
 
@@ -864,6 +886,7 @@ int ad4cl_cuda_kernel_set_arg_params(ad4cl_kernel* k, int index, int first_id, i
     a->count = count;
     a->buf = nullptr;
     a->set = true;
+    k->drop_graphs();
     return AD4CL_OK;
 }
 
@@ -909,26 +932,60 @@ int ad4cl_cuda_check(ad4cl_kernel* k) {
     return status_to_error(k, *k->status_pinned);
 }
 
+/* the host path on the stream: parameters up, launches, [grad, f, ops, slots, status] down */
+static int enqueue_host_path(ad4cl_kernel* k, int want_gradient) {
+    cudaStream_t st = k->ctx->stream;
+    const int P = k->nparams;
+    if (P > 0)
+        CUDA_TRY(cudaMemcpyAsync(k->params_dev, k->params_pinned, sizeof (struct ad_variable) * (size_t) P,
+                cudaMemcpyHostToDevice, st));
+    int rc = enqueue(k, nullptr, k->result_dev, want_gradient, 1, k->result_dev + P + 3);
+    if (rc != AD4CL_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(k->result_pinned, k->result_dev, sizeof (double) * (size_t) (P + 4), cudaMemcpyDeviceToHost, st));
+    return AD4CL_OK;
+}
+
 int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f, double* grad) {
     if (!k || !f || (!theta && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(k->ctx->device));
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
     cudaStream_t st = k->ctx->stream;
-    const int ncols = nparams + 3;
-    if (nparams > 0) {
-        memcpy(k->theta_pinned, theta, sizeof (double) * (size_t) nparams);
-        CUDA_TRY(cudaMemcpyAsync(k->theta_dev, k->theta_pinned, sizeof (double) * (size_t) nparams, cudaMemcpyHostToDevice, st));
+    const int want = grad != nullptr ? 1 : 0;
+    for (int p = 0; p < nparams; p++) { /* ad_init_var, ad4cl.h:90-93: {value, id = p} */
+        k->params_pinned[p].value = theta[p];
+        k->params_pinned[p].id = p;
     }
-    CUDA_TRY(cudaEventRecord(k->ev0, st));
-    rc = enqueue(k, k->theta_dev, k->result_dev, grad != nullptr, 1);
-    if (rc != AD4CL_OK) return rc;
-    CUDA_TRY(cudaEventRecord(k->ev1, st));
-    CUDA_TRY(cudaMemcpyAsync(k->result_pinned, k->result_dev, sizeof (double) * (size_t) ncols, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(k->status_pinned, k->status_dev, sizeof (int), cudaMemcpyDeviceToHost, st));
+    /* Replay the whole evaluation as one CUDA graph (captured on first use; the launches'
+       arguments are fixed until an argument or the configuration changes).  Profiling needs
+       events around the fused kernel, so it takes the plain path. */
+    const bool use_graph = !k->profiling && !k->graph_disabled;
+    if (use_graph && !k->graph[want]) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = enqueue_host_path(k, want);
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (rc == AD4CL_OK && e == cudaSuccess && g && cudaGraphInstantiate(&k->graph[want], g, 0) != cudaSuccess)
+                k->graph[want] = nullptr;
+            if (g) cudaGraphDestroy(g);
+        }
+        if (!k->graph[want]) { /* capture unavailable on this stream: fall back to plain launches for good */
+            cudaGetLastError();
+            k->graph_disabled = true;
+        }
+    }
+    if (use_graph && k->graph[want]) {
+        CUDA_TRY(cudaGraphLaunch(k->graph[want], st));
+        k->stats.kernel_ms = 0.f;
+    } else {
+        CUDA_TRY(cudaEventRecord(k->ev0, st));
+        rc = enqueue_host_path(k, want);
+        if (rc != AD4CL_OK) return rc;
+        CUDA_TRY(cudaEventRecord(k->ev1, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaEventElapsedTime(&k->stats.kernel_ms, k->ev0, k->ev1));
-    rc = status_to_error(k, *k->status_pinned);
+    if (!(use_graph && k->graph[want])) CUDA_TRY(cudaEventElapsedTime(&k->stats.kernel_ms, k->ev0, k->ev1));
+    rc = status_to_error(k, (int) k->result_pinned[nparams + 3]);
     if (rc != AD4CL_OK) return rc;
     *f = k->result_pinned[nparams];
     if (grad) memcpy(grad, k->result_pinned, sizeof (double) * (size_t) nparams);
