@@ -42,6 +42,16 @@ class KernelConfig(ctypes.Structure):
                 ("blocks_per_sm", c_int), ("reference_quirks", c_int)]
 
 
+class LbfgsOptions(ctypes.Structure):
+    _fields_ = [("max_iterations", c_int), ("max_linesearch_iterations", c_int), ("history", c_int),
+                ("gradient_tolerance", c_double), ("function_tolerance", c_double)]
+
+
+class LbfgsResult(ctypes.Structure):
+    _fields_ = [("f", c_double), ("gradient_max", c_double), ("converged", c_int), ("iterations", c_int),
+                ("linesearch_iteration", c_int), ("evaluations", c_int), ("number_of_parameters", c_int)]
+
+
 class EvalStats(ctypes.Structure):
     _fields_ = [("ops", c_double), ("slots", c_double), ("grid", c_int), ("block", c_int),
                 ("smem_bytes", c_size_t), ("arena_bytes", c_size_t), ("kernel_ms", c_float)]
@@ -91,6 +101,8 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
     lib.ad4cl_cuda_kernel_profile.argtypes = [c_void_p, c_int]
+    lib.ad4cl_cuda_lbfgs_options_default.argtypes = [POINTER(LbfgsOptions)]
+    lib.ad4cl_cuda_minimize_lbfgs.argtypes = [c_void_p, c_void_p, c_int, POINTER(LbfgsOptions), POINTER(LbfgsResult)]
     lib.ad4cl_cuda_matrix_product_dense.argtypes = [c_void_p, c_int, c_int] + [c_void_p] * 8
     lib.ad4cl_cuda_comm_create.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]
     lib.ad4cl_cuda_comm_handle.argtypes = [c_void_p, c_void_p]
@@ -235,6 +247,16 @@ class Kernel:
 
     def check(self) -> None:
         _check(lib.ad4cl_cuda_check(self._h))
+
+    def minimize(self, theta0, **options):
+        """L-BFGS inside the library (ad4cl_cuda_minimize_lbfgs) -> (theta, dict of the result fields)."""
+        th = np.array(theta0, dtype=np.float64, copy=True)
+        opt, res = LbfgsOptions(), LbfgsResult()
+        _check(lib.ad4cl_cuda_lbfgs_options_default(byref(opt)))
+        for key, v in options.items():
+            setattr(opt, key, v)
+        _check(lib.ad4cl_cuda_minimize_lbfgs(self._h, th.ctypes.data, len(th), byref(opt), byref(res)))
+        return th, {name: getattr(res, name) for name, _ in LbfgsResult._fields_}
 
     def stats(self) -> dict:
         s = EvalStats()

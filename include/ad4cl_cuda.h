@@ -192,6 +192,34 @@ int ad4cl_cuda_kernel_profile(ad4cl_kernel* kernel, int enable);
 int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* kernel, double* mean_ms, long long* launches, int reset);
 
 /*
+ * L-BFGS over ad4cl_cuda_eval: the optimiser the reference declares for its device runtime
+ * (struct lbfgs_parameters_g / lbfgs_update_g, ad.cl:99-127) and never defines; its examples
+ * are driven by ADMB's function_minimizer instead (test/admb/simple.cpp:481-492).  Field names
+ * follow the reference's struct.  theta: start point in, minimiser out.
+ */
+typedef struct ad4cl_lbfgs_options {
+    int max_iterations;              /* ad.cl:106 */
+    int max_linesearch_iterations;   /* ad.cl:108 */
+    int history;                     /* correction pairs kept (m) */
+    double gradient_tolerance;       /* stop when max |g_i| <= this */
+    double function_tolerance;       /* stop when f decreases by <= this * max(1, |f|) */
+} ad4cl_lbfgs_options;
+
+typedef struct ad4cl_lbfgs_result {
+    double f;                        /* objective at the returned point */
+    double gradient_max;             /* max |g_i| there */
+    int converged;                   /* ad.cl:105: 1 gradient, 2 function tolerance, 0 iteration limit, -1 line search failed */
+    int iterations;
+    int linesearch_iteration;        /* ad.cl:107: line-search evaluations in total */
+    int evaluations;                 /* objective+gradient evaluations (ad4cl_cuda_eval calls) */
+    int number_of_parameters;        /* ad.cl:110 */
+} ad4cl_lbfgs_result;
+
+int ad4cl_cuda_lbfgs_options_default(ad4cl_lbfgs_options* options);
+int ad4cl_cuda_minimize_lbfgs(ad4cl_kernel* kernel, double* theta, int number_of_parameters,
+        const ad4cl_lbfgs_options* options, ad4cl_lbfgs_result* result);
+
+/*
  * Dense-contraction path for test/matrix (matrix_mul.cpp:39-57, matrixmul.cl:5-28): instead of
  * recording 2n AD operators per element of C = A*B, compute C, sum C and the derivative of
  * L = sum_{j,i} G[j,i] C[j,i] as two more products, dL/dA = G*B^T and dL/dB = A^T*G.

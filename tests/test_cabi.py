@@ -65,8 +65,9 @@ def test_struct_layouts_match_header():
     src = r'''
 #include <stdio.h>
 #include "ad4cl_cuda.h"
-int main(void) { printf("%zu %zu %zu %zu\n", sizeof(ad4cl_kernel_config), sizeof(ad4cl_eval_stats),
-    __builtin_offsetof(ad4cl_kernel_config, epilogue_n), __builtin_offsetof(ad4cl_eval_stats, kernel_ms)); return 0; }
+int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ad4cl_kernel_config), sizeof(ad4cl_eval_stats),
+    __builtin_offsetof(ad4cl_kernel_config, epilogue_n), __builtin_offsetof(ad4cl_eval_stats, kernel_ms),
+    sizeof(ad4cl_lbfgs_options), sizeof(ad4cl_lbfgs_result)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -75,6 +76,7 @@ int main(void) { printf("%zu %zu %zu %zu\n", sizeof(ad4cl_kernel_config), sizeof
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(REPO, "include"), c, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert int(out[0]) == ctypes.sizeof(host.KernelConfig)
+    assert int(out[4]) == ctypes.sizeof(host.LbfgsOptions) and int(out[5]) == ctypes.sizeof(host.LbfgsResult)
     assert int(out[1]) == ctypes.sizeof(host.EvalStats)
     assert int(out[2]) == host.KernelConfig.epilogue_n.offset
     assert int(out[3]) == host.EvalStats.kernel_ms.offset

@@ -97,3 +97,35 @@ def test_optimiser_drives_the_cuda_path():
     assert np.abs(res.x - truth).max() < np.abs(start - truth).max()          # closer to the generating parameters
     assert np.abs(res.jac).max() < 1e-3 * n                                   # gradient per observation ~ 0
     assert evals < 1500
+
+
+@pytest.mark.gpu
+def test_library_lbfgs_recovers_the_regression_line(ctx):
+    """ad4cl_cuda_minimize_lbfgs on the simple.cpp recipe (y = 2 x + 4 + 7 N(0,1)): the soft goldens of
+    the reference's ADMB fits are a -> 2, b -> 4 (test/admb/*/simple.par); compared here with the
+    closed-form least-squares line of the same data, which minimises (n/2) log sum r^2 exactly."""
+    from ad4cl_b200 import workloads as W
+    n = 100003
+    w = W.describe("linreg2_simple", n)
+    k = W.bind(ctx, w)
+    theta, res = k.minimize(w.theta, gradient_tolerance=1e-7)
+    k.free()
+    x, y = w.d0, w.d1
+    a_ls, b_ls = np.polyfit(x, y, 1)
+    assert res["converged"] in (1, 2) and res["evaluations"] < 200
+    assert abs(theta[0] - a_ls) < 1e-6 and abs(theta[1] - b_ls) < 1e-5
+    assert abs(theta[0] - 2.0) < 0.01 and abs(theta[1] - 4.0) < 0.2
+
+
+@pytest.mark.gpu
+def test_library_lbfgs_matches_scipy_on_catch_at_age(ctx):
+    from scipy.optimize import minimize
+    from ad4cl_b200 import workloads as W
+    w = W.describe("catch_at_age", 200_000)
+    k = W.bind(ctx, w)
+    theta, res = k.minimize(w.theta, max_iterations=400, gradient_tolerance=1e-4)
+    ref = minimize(lambda t: k.eval(t), w.theta, jac=True, method="L-BFGS-B",
+                   options={"maxiter": 400, "ftol": 1e-15, "gtol": 1e-4})
+    k.free()
+    assert res["f"] <= ref.fun + 1e-6 * abs(ref.fun)       # at least as low as scipy's minimum
+    assert np.abs(theta - ref.x).max() < 0.05
