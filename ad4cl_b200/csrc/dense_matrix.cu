@@ -212,6 +212,17 @@ __global__ void sum_fixed_order(const double* __restrict__ v, int n, double* out
     }
 }
 
+/* fp64 FMA microbenchmark: 8 independent chains per thread, the denominator for the dense path */
+__global__ void __launch_bounds__(256) dfma_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 template <bool TA, bool TB>
 cudaError_t gemm(int variant, const double* A, const double* B, double* C, int n, double* block_sums, cudaStream_t st) {
     dim3 grid(n / BN, n / BM);
@@ -264,6 +275,32 @@ int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, cons
         snprintf(msg, sizeof msg, "dense matrix product failed: %s", cudaGetErrorString(e));
         return ad4cl_cuda_set_error_(AD4CL_ERR_CUDA, msg);
     }
+    return AD4CL_OK;
+}
+/* Measured fp64 FMA rate of the device in TFLOP/s (2 flop per DFMA), the roofline denominator
+   SURVEY.md 8(d) asks to measure rather than quote.  Synchronous; ~20 ms. */
+int ad4cl_cuda_measure_fp64_peak(ad4cl_context* ctx, double* tflops) {
+    if (!ctx || !tflops) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "NULL argument");
+    cudaStream_t st = (cudaStream_t) ad4cl_cuda_stream(ctx);
+    const int blocks = 148 * 8, threads = 256, iters = 20000;
+    double* out = nullptr;
+    cudaEvent_t e0, e1;
+    cudaError_t e = cudaMalloc(&out, sizeof (double) * blocks * threads);
+    if (e != cudaSuccess) return ad4cl_cuda_set_error_(AD4CL_ERR_NOMEM, cudaGetErrorString(e));
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dfma_peak<<<blocks, threads, 0, st>>>(out, 1000);
+    cudaEventRecord(e0, st);
+    dfma_peak<<<blocks, threads, 0, st>>>(out, iters);
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return ad4cl_cuda_set_error_(AD4CL_ERR_CUDA, cudaGetErrorString(e));
+    *tflops = 2.0 * 8.0 * iters * (double) blocks * threads / (ms * 1e-3) / 1e12;
     return AD4CL_OK;
 }
 #pragma GCC visibility pop

@@ -101,6 +101,7 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
     lib.ad4cl_cuda_kernel_profile.argtypes = [c_void_p, c_int]
+    lib.ad4cl_cuda_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
     lib.ad4cl_cuda_lbfgs_options_default.argtypes = [POINTER(LbfgsOptions)]
     lib.ad4cl_cuda_minimize_lbfgs.argtypes = [c_void_p, c_void_p, c_int, POINTER(LbfgsOptions), POINTER(LbfgsResult)]
     lib.ad4cl_cuda_matrix_product_dense.argtypes = [c_void_p, c_int, c_int] + [c_void_p] * 8
@@ -369,6 +370,12 @@ class Context:
         p = lambda b: None if b is None else b.device_ptr  # noqa: E731
         _check(lib.ad4cl_cuda_matrix_product_dense(self._h, variant, n, p(A), p(B), p(G), p(C), p(dA), p(dB),
                                                    p(total), p(workspace)))
+
+    def measure_fp64_peak(self) -> float:
+        """Measured fp64 FMA rate in TFLOP/s (microbenchmark, ~20 ms)."""
+        v = c_double()
+        _check(lib.ad4cl_cuda_measure_fp64_peak(self._h, byref(v)))
+        return v.value
 
     def synchronize(self) -> None:
         """Wait for everything queued on the context's stream (a 0-byte blocking download)."""

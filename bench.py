@@ -337,7 +337,9 @@ def main():
         pass
     stats = k.stats()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": f"{w.kernel}__entry (fused record+sweep+block reduce)",
+                "traffic": traffic, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "input_stream": {"bytes": w.input_bytes, "GBps": w.input_bytes / (kernel_ms * 1e-3) / 1e9,
+                                 "frac": w.input_bytes / (kernel_ms * 1e-3) / 1e9 / peak}, "kernel": f"{w.kernel}__entry (fused record+sweep+block reduce)",
                 "kernel_ms": kernel_ms, "kernel_ms_by_rank": kernel_ms_by_rank, "kernel_launches_timed": kernel_launches,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = 24 B x operand slots + inputs + 8(P+1) (SURVEY 8d); the arena of "

@@ -24,7 +24,7 @@ def main(n=1024, reps=10):
     tot = torch.zeros(1, dtype=torch.float64, device="cuda")
     ws = torch.empty(n * n + (n // 64) ** 2, dtype=torch.float64, device="cuda")
     wrap = lambda t: ctx.wrap(t.data_ptr(), t.numel() * 8)  # noqa: E731
-    out = {"n": n}
+    out = {"n": n, "fp64_fma_peak_tflops_measured": ctx.measure_fp64_peak()}
     for variant, name in ((0, "dense_dfma"), (1, "dense_dmma")):
         def step():
             ctx.matrix_product_dense(n, wrap(A_t), wrap(B_t), C=wrap(C_t), dA=wrap(dA_t), dB=wrap(dB_t),

@@ -232,6 +232,9 @@ int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, cons
         const double* B_dev, const double* G_dev, double* C_dev, double* dA_dev, double* dB_dev,
         double* sum_dev, double* workspace_dev);
 
+/* measured fp64 FMA rate of the device in TFLOP/s: the denominator of the dense path's roofline */
+int ad4cl_cuda_measure_fp64_peak(ad4cl_context* ctx, double* tflops);
+
 /*
  * Multi-GPU (one process per GPU; no counterpart in the reference, which is single device):
  * a one-shot all-reduce of the short result vector [grad..., S, ops, slots] over NVLink peer

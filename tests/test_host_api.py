@@ -129,3 +129,19 @@ def test_library_lbfgs_matches_scipy_on_catch_at_age(ctx):
     k.free()
     assert res["f"] <= ref.fun + 1e-6 * abs(ref.fun)       # at least as low as scipy's minimum
     assert np.abs(theta - ref.x).max() < 0.05
+
+
+@pytest.mark.gpu
+def test_benchmarks_txt_objective_value(ctx):
+    """test/admb/benchmarks.txt:9-11: all three gradient methods end at f = 8.8535e+006 for
+    N = 1 000 003 observations of y = 2 x + 4 + 7 N(0,1).  The data there come from ADMB's RNG
+    (not reproducible), but the value is determined by the recipe: f* = (N/2) ln(sum r^2) with
+    sum r^2 ~ 49 N.  Our fit of a freshly generated sample must land on the same five digits."""
+    from ad4cl_b200 import workloads as W
+    n = 1_000_003
+    w = W.describe("linreg2_simple", n)
+    k = W.bind(ctx, w)
+    theta, res = k.minimize(w.theta, gradient_tolerance=1e-6)
+    k.free()
+    assert abs(res["f"] - 8.8535e6) <= 2e-4 * 8.8535e6
+    assert abs(theta[0] - 1.99987523364) < 5e-4 and abs(theta[1] - 4.02338318012) < 0.06   # dist/.../simple.par:1-5
