@@ -276,9 +276,14 @@ class Kernel:
         return ms.value, n.value
 
     def free(self) -> None:
+        """Release the kernel and the data buffers workloads.bind() uploaded for it."""
         if self._h:
             lib.ad4cl_cuda_kernel_free(self._h)
             self._h = None
+        for b in getattr(self, "_buffers", ()) or ():
+            if b is not None:
+                b.free()
+        self._buffers = ()
 
 
 class Comm:
