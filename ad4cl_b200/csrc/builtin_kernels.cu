@@ -13,10 +13,12 @@
  */
 #include "ad4cl_opencl_compat.cuh"
 #include "ad4cl_builtin.h"
+#include "ad4cl_var.cuh"
 
 #include "../kernels/objectives.cl"
 #include "../kernels/matrix.cl"
 #include "../kernels/op_probe.cl"
+#include "../kernels/var_kernels.cl"
 
 #define OBJECTIVE_ABI(NAME)                                                                  \
     AD4CL_OBJECTIVE_ENTRY(NAME,                                                               \
@@ -29,6 +31,10 @@ AD4CL_OBJECTIVE_ENTRY(linreg2_g,
 AD4CL_OBJECTIVE_ENTRY(linreg2_p,
     (const struct ad_variable* a, const struct ad_variable* b, double* x, double* y, int size),
     (gs, gradient_stack, a, b, x, y, out, size))
+AD4CL_OBJECTIVE_ENTRY(linreg2_var,
+    (struct ad_variable* a, struct ad_variable* b, double* x, double* y, int size),
+    (gs, gradient_stack, a, b, x, y, out, size))
+OBJECTIVE_ABI(regression_logistic_var)
 OBJECTIVE_ABI(regression_linear)
 OBJECTIVE_ABI(regression_logistic)
 OBJECTIVE_ABI(catch_at_age)
@@ -49,6 +55,8 @@ AD4CL_OBJECTIVE_ENTRY(matrix_elementwise,
 extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(linreg2_g, "GSVVDDOi"),
     ROW(linreg2_p, "GSVVDDOi"),
+    ROW(linreg2_var, "GSVVDDOi"),
+    ROW(regression_logistic_var, "GSVDDOiii"),
     ROW(regression_linear, "GSVDDOiii"),
     ROW(regression_logistic, "GSVDDOiii"),
     ROW(catch_at_age, "GSVDDOiii"),

@@ -128,3 +128,43 @@ def test_matrix_ragged_and_invalid_shapes(ctx, oracle_api):
         k2.eval([1.0])
     assert e.value.code == host.ERR_INVALID and "not set" in str(e.value)
     k.free()
+
+
+def test_var_operators_are_the_function_calls(ctx):
+    """ad4cl::var (device-side Variable.hpp): objectives written with operators record the same tape
+    and return the same bits as their ad_* function-call forms."""
+    from ad4cl_b200 import host
+    w = W.describe("linreg2_main", 10007)
+    res = {}
+    for name in ("linreg2_g", "linreg2_var"):
+        k = ctx.builtin(name)
+        k.set_args(None, None, host.params(0), host.params(1), ctx.buffer(w.d0), ctx.buffer(w.d1), None, w.size)
+        k.configure(w.size, max_ops=4, max_slots=6, epilogue="half_n_log")
+        res[name] = k.eval(w.theta) + (k.stats()["slots"],)
+        k.free()
+    assert res["linreg2_g"][0] == res["linreg2_var"][0] and np.array_equal(res["linreg2_g"][1], res["linreg2_var"][1])
+    assert res["linreg2_g"][2] == res["linreg2_var"][2]
+    w = W.describe("regression_logistic", 3001)
+    out = []
+    for name in ("regression_logistic", "regression_logistic_var"):
+        w.kernel = name
+        k = W.bind(ctx, w)
+        out.append(k.eval(w.theta))
+        k.free()
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
+def test_var_kernel_through_the_jit(ctx):
+    """#include "ad4cl_var.cuh" is available to JIT-compiled kernels as well."""
+    from ad4cl_b200 import host
+    src = '#include "ad4cl_var.cuh"\n' + open(os.path.join(REPO, "ad4cl_b200", "kernels", "var_kernels.cl")).read()
+    k = ctx.from_source(src, "linreg2_var", "GSVVDDOi")
+    w = W.describe("linreg2_main", 1000)
+    k.set_args(None, None, host.params(0), host.params(1), ctx.buffer(w.d0), ctx.buffer(w.d1), None, w.size)
+    k.configure(w.size, max_ops=4, max_slots=6, epilogue="half_n_log")
+    f, g = k.eval(w.theta)
+    k.free()
+    kb = W.bind(ctx, w)
+    fb, gb = kb.eval(w.theta)
+    kb.free()
+    assert f == fb and np.array_equal(g, gb)
