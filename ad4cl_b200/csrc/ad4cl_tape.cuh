@@ -61,7 +61,16 @@ enum Status : int {
     kOk = 0,
     kErrTapeOverflow = 1,   /* more slots than the arena column holds */
     kErrWindow = 2,         /* far operand met while the far plane is disabled */
+    kErrBounds = 8,         /* AD4CL_DEBUG_BOUNDS build: an arena access left this thread's column */
 };
+
+/* Self-checking build (make EXTRA=-DAD4CL_DEBUG_BOUNDS=1): every arena access is range-checked
+   against the thread's own column and skipped + reported instead of executed.  compute-sanitizer
+   is not available on the GPU pool this was developed on; the GPU test-suite is run against this
+   build instead. */
+#ifndef AD4CL_DEBUG_BOUNDS
+#define AD4CL_DEBUG_BOUNDS 0
+#endif
 
 struct ThreadTape {
     char* cur;            /* address of this lane's partial in the next free row */
@@ -73,6 +82,9 @@ struct ThreadTape {
     int wm1;              /* W - 1, W a power of two */
     int nops;             /* operators recorded by the current work-item (statistics) */
     char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
+#if AD4CL_DEBUG_BOUNDS
+    int cap_rows;         /* rows of this column including the guard rows */
+#endif
     int status;           /* sticky Status bits */
     long long total_ops;  /* statistics over all work-items of this thread */
     long long total_slots;
@@ -97,6 +109,9 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
     t.wm1 = window - 1;
     t.nops = 0;
     t.far_adj = far ? warp_region + (size_t) (cap_slots + kGuardRows) * kRowBytes + lane * 8 : nullptr;
+#if AD4CL_DEBUG_BOUNDS
+    t.cap_rows = (int) cap_slots + kGuardRows;
+#endif
     t.status = kOk;
     t.total_ops = 0;
     t.total_slots = 0;
@@ -108,6 +123,9 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
    no return value: it is issued as a fire-and-forget reduction. */
 __device__ __forceinline__ int tape_note_far(ThreadTape* t, int pos) {
     if (t->far_adj == nullptr) return kErrWindow;
+#if AD4CL_DEBUG_BOUNDS
+    if (pos < 0 || pos >= t->next_id - t->first_temp) return kErrBounds;
+#endif
     atomicOr(reinterpret_cast<int*> (t->begin + (size_t) pos * kRowBytes + t->id_off), kHasFarFlag);
     return kOk;
 }
@@ -130,6 +148,13 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
             word |= kFarFlag;
         }
     }
+#if AD4CL_DEBUG_BOUNDS
+    if (t->cur < t->begin || t->cur >= t->begin + (size_t) t->cap_rows * kRowBytes
+            || (size_t) (t->cur - t->begin) != (size_t) (t->next_id - t->first_temp) * kRowBytes) {
+        t->status |= kErrBounds;
+        return;
+    }
+#endif
     *reinterpret_cast<double*> (t->cur) = dx;
     *reinterpret_cast<int*> (t->cur + t->id_off) = word;
     t->cur += kRowBytes;
@@ -265,6 +290,12 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
     }
     const char* cur = t.begin + (size_t) rows * kRowBytes;
 
+#if AD4CL_DEBUG_BOUNDS
+    if (rows < 0 || rows > t.cap_rows) {
+        t.status |= kErrBounds;
+        return;
+    }
+#endif
     double w = 0.0;
     /* the first batch takes the rows that do not fill a whole batch */
     double dx_now[U], dx_next[U];
@@ -313,6 +344,12 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
                 w = lds_f64(r);
                 sts_f64(r, 0.0);
                 if (idw & kHasFarFlag) {
+#if AD4CL_DEBUG_BOUNDS
+                    if (far_adj == nullptr || me < 0 || me >= t.cap_rows) {
+                        t.status |= kErrBounds;
+                        return;
+                    }
+#endif
                     double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
                     w += *fa;
                     *fa = 0.0;
@@ -321,6 +358,20 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
             const int payload = idw & kIdMask;
             const double c = w * dx_now[j];
             const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
+#if AD4CL_DEBUG_BOUNDS
+            if ((cls == 0 || cls == kFarFlag) && (payload < 0 || payload >= idx - 1 - j)) { /* operands precede their use */
+                t.status |= kErrBounds;
+                return;
+            }
+            if (cls == kParamFlag && payload >= t.first_temp) {
+                t.status |= kErrBounds;
+                return;
+            }
+            if (fetch && cur < t.begin) {
+                t.status |= kErrBounds;
+                return;
+            }
+#endif
             if (cls == 0) {
                 const unsigned a = T.ring + (unsigned) (payload & wmask) * T.stride;
                 sts_f64(a, lds_f64(a) + c);

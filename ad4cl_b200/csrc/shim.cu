@@ -486,6 +486,8 @@ int status_to_error(ad4cl_kernel* k, int st) {
     if (k->arena) cudaMemsetAsync(k->arena, 0, k->arena_bytes, k->ctx->stream);
     cudaMemsetAsync(k->status_dev, 0, sizeof (int), k->ctx->stream);
     cudaStreamSynchronize(k->ctx->stream);
+    if (st & ad4cl::kErrBounds)
+        return fail(AD4CL_ERR_CUDA, "kernel %s: internal bounds check failed (AD4CL_DEBUG_BOUNDS build)", k->name.c_str());
     if (st & ad4cl::kErrTapeOverflow)
         return fail(AD4CL_ERR_TAPE_OVERFLOW, "kernel %s: a work-item recorded more than max_ops=%d operators / %u slots "
                 "(the reference overflows its stack silently here, SURVEY Q8)", k->name.c_str(), k->cfg.max_ops, k->L.cap_slots);
