@@ -42,6 +42,9 @@ struct LaunchInfo {
     double* partials;       /* [gridDim.x][ncols]; ncols = nparams + 3, or 3 with kAccGlobal: [grad..., sum, ops, slots] */
     double* global_grad;    /* kAccGlobal target, else null */
     int* status;            /* OR of Status bits */
+    double* retain_meta;    /* non-null: RECORD ONLY.  One work-group per CTA (grid = number of groups), no
+                               sweep, every thread keeps its tape in its own arena column and writes
+                               {out.value, out.id, slots} here, 3 doubles per work-item (tape export path) */
 };
 
 /* Per-thread NDRange coordinates, published for get_global_id() and friends. */
@@ -170,6 +173,13 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         struct ad_variable outv = {0.0, kNoId};
         body(&gs, &outv - item);
         sum += outv.value;
+        if (L.retain_meta != nullptr) { /* tape export: leave the rows in the arena for the host */
+            double* m = L.retain_meta + 3 * item;
+            m[0] = outv.value;
+            m[1] = (double) outv.id;
+            m[2] = (double) (tape.next_id - tape.first_temp);
+            continue;
+        }
         /* a thread whose tape overflowed skips the sweep (the host reports the error) */
         if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) tape_sweep<MODE>(tape, outv.id, T);
         tape_rewind(tape);

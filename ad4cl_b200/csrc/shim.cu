@@ -1106,6 +1106,132 @@ int ad4cl_cuda_comm_destroy(ad4cl_comm* c) {
     return AD4CL_OK;
 }
 
+/*
+ * Tape export (debug / legacy path).  Records only -- no sweep -- with one arena column per WORK-ITEM,
+ * copies the rows to the host and rewrites them as the reference's 40-byte entries (ad.cl:75-79) in
+ * work-item order, i.e. the stack a serial run of the reference would have produced, so that legacy host
+ * code (host sum of out[], epilogue, compute_gradient: simple.cpp:357-369) keeps working unchanged.
+ * Ids: independents keep theirs; the temporaries of work-item i become first_free_id + (operators of
+ * the work-items before i) + operator index.  In-place operators appear with a fresh result id (same
+ * sweep result); a leaf (ad_init_var_g) appears as an entry of size 0.  Small problems only: the arena
+ * holds n_items * (max_slots + 2) * 12 bytes.
+ */
+int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, int first_free_id,
+        void* entries_out, long long capacity, long long* n_entries, void* out_vars, long long n_out) {
+    struct HostEntry { double dx0; int id0; int pad0; double dx1; int id1; int pad1; int id; int size; };
+    struct HostVar { double value; int id; int pad; };
+    static_assert(sizeof (HostEntry) == 40 && sizeof (HostVar) == 16, "reference layouts (ad.cl:65-79)");
+    if (!k || !entries_out || !n_entries || (!theta && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    int rc = prepare(k, nparams);
+    if (rc != AD4CL_OK) return rc;
+    cudaStream_t st = k->ctx->stream;
+    const long long items = k->L.n_items;
+    const int B = k->block, nw = B / 32;
+    const long long ngroups = (items + B - 1) / B;
+    const size_t region = k->L.warp_region;
+    const size_t arena_bytes = (size_t) ngroups * nw * region;
+    if (arena_bytes > ((size_t) 8 << 30))
+        return fail(AD4CL_ERR_NOMEM, "tape export of %lld work-items needs a %zu-byte arena: this path is for small problems", items, arena_bytes);
+    char* arena = nullptr;
+    double *meta = nullptr, *partials = nullptr;
+    CUDA_TRY(cudaMalloc(&arena, arena_bytes));
+    CUDA_TRY(cudaMemsetAsync(arena, 0, arena_bytes, st));
+    CUDA_TRY(cudaMalloc(&meta, sizeof (double) * 3 * (size_t) items));
+    CUDA_TRY(cudaMemsetAsync(meta, 0, sizeof (double) * 3 * (size_t) items, st));
+    CUDA_TRY(cudaMalloc(&partials, sizeof (double) * (size_t) ngroups * (nparams + 3)));
+
+    /* record-only launch: same entry, one work-group per CTA, private arena */
+    const ad4cl::LaunchInfo saved = k->L;
+    const int saved_grid = k->grid;
+    double* const saved_partials = k->partials;
+    k->partials = partials;
+    k->L.arena = arena;
+    k->L.partials = partials;
+    k->L.retain_meta = meta;
+    k->L.tape_in_smem = 0;
+    k->grid = (int) ngroups;
+    for (int p = 0; p < nparams; p++) {
+        k->params_pinned[p].value = theta[p];
+        k->params_pinned[p].id = p;
+    }
+    if (nparams > 0)
+        CUDA_TRY(cudaMemcpyAsync(k->params_dev, k->params_pinned, sizeof (struct ad_variable) * (size_t) nparams, cudaMemcpyHostToDevice, st));
+    rc = enqueue(k, nullptr, k->result_dev, 1, 0);
+    k->L = saved;
+    k->grid = saved_grid;
+    k->partials = saved_partials;
+    std::vector<char> rows(arena_bytes);
+    std::vector<double> m(3 * (size_t) items);
+    if (rc == AD4CL_OK) {
+        cudaError_t e = cudaMemcpyAsync(rows.data(), arena, arena_bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m.data(), meta, sizeof (double) * m.size(), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(k->status_pinned, k->status_dev, sizeof (int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(AD4CL_ERR_CUDA, "tape export copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(arena);
+    cudaFree(meta);
+    cudaFree(partials);
+    if (rc != AD4CL_OK) return rc;
+    rc = status_to_error(k, *k->status_pinned);
+    if (rc != AD4CL_OK) return rc;
+
+    /* rows -> reference entries, work-item by work-item */
+    HostEntry* E = static_cast<HostEntry*> (entries_out);
+    HostVar* O = static_cast<HostVar*> (out_vars);
+    long long ne = 0;
+    int next_id = first_free_id;
+    std::vector<int> op_of_slot;
+    for (long long item = 0; item < items; item++) {
+        /* work-item -> (CTA, thread): the NDRange walk of run_objective (1-D and 2-D) */
+        const int g0 = k->L.g0, l0 = k->L.l0, l1 = B / l0;
+        const long long gid0 = item % g0, gid1 = item / g0;
+        const long long grp = (gid1 / l1) * (g0 / l0) + gid0 / l0;
+        const int tid = (int) ((gid1 % l1) * l0 + gid0 % l0);
+        const char* col = rows.data() + ((size_t) grp * nw + tid / 32) * region;
+        const int lane = tid % 32;
+        const int nslots = (int) m[3 * item + 2];
+        op_of_slot.assign((size_t) nslots, -1);
+        const int base = next_id;
+        int op = 0;
+        HostEntry cur{};
+        int have = 0;
+        for (int s = 0; s < nslots; s++) {
+            const char* row = col + (size_t) s * ad4cl::kRowBytes;
+            double dx;
+            int word;
+            memcpy(&dx, row + lane * 8, 8);
+            memcpy(&word, row + ad4cl::kRowIdOffset + lane * 4, 4);
+            if (!(word & ad4cl::kNopFlag)) {
+                const int payload = word & ad4cl::kIdMask;
+                const int id = (word & ad4cl::kParamFlag) ? payload : base + op_of_slot[(size_t) payload];
+                if (have == 0) { cur.dx0 = dx; cur.id0 = id; }
+                else { cur.dx1 = dx; cur.id1 = id; }
+                have++;
+            }
+            if (word & ad4cl::kEndFlag) {
+                if (ne >= capacity) return fail(AD4CL_ERR_TAPE_OVERFLOW, "the exported tape exceeds the caller's %lld entries", capacity);
+                cur.id = base + op;
+                cur.size = have;
+                E[ne++] = cur;
+                op_of_slot[(size_t) s] = op++;
+                cur = HostEntry{};
+                have = 0;
+            }
+        }
+        next_id = base + op;
+        if (O && item < n_out) {
+            const int oid = (int) m[3 * item + 1];
+            O[item].value = m[3 * item];
+            O[item].id = oid < 0 ? 0 : (oid < nparams ? oid : base + op_of_slot[(size_t) (oid - nparams)]);
+            O[item].pad = 0;
+        }
+    }
+    *n_entries = ne;
+    return AD4CL_OK;
+}
+
 int ad4cl_cuda_last_stats(ad4cl_kernel* k, ad4cl_eval_stats* stats) {
     if (!k || !stats) return fail(AD4CL_ERR_INVALID, "NULL argument");
     *stats = k->stats;

@@ -101,6 +101,7 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_last_stats.argtypes = [c_void_p, POINTER(EvalStats)]
     lib.ad4cl_cuda_kernel_profile.argtypes = [c_void_p, c_int]
+    lib.ad4cl_cuda_export_tape.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_longlong, POINTER(c_longlong), c_void_p, c_longlong]
     lib.ad4cl_cuda_measure_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
     lib.ad4cl_cuda_lbfgs_options_default.argtypes = [POINTER(LbfgsOptions)]
     lib.ad4cl_cuda_minimize_lbfgs.argtypes = [c_void_p, c_void_p, c_int, POINTER(LbfgsOptions), POINTER(LbfgsResult)]
@@ -248,6 +249,21 @@ class Kernel:
 
     def check(self) -> None:
         _check(lib.ad4cl_cuda_check(self._h))
+
+    def export_tape(self, theta, n_out: int, capacity: int, first_free_id: int | None = None):
+        """Record without sweeping and return (entries, out): numpy structured arrays in the
+        reference's layouts (40-byte ad_entry, 16-byte ad_variable)."""
+        entry_t = np.dtype([("dx0", "<f8"), ("id0", "<i4"), ("_p0", "<i4"), ("dx1", "<f8"), ("id1", "<i4"),
+                            ("_p1", "<i4"), ("id", "<i4"), ("size", "<i4")])
+        var_t = np.dtype([("value", "<f8"), ("id", "<i4"), ("_p", "<i4")])
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        entries = np.zeros(capacity, dtype=entry_t)
+        out = np.zeros(n_out, dtype=var_t)
+        n = c_longlong()
+        ffi = len(th) if first_free_id is None else first_free_id
+        _check(lib.ad4cl_cuda_export_tape(self._h, th.ctypes.data, len(th), ffi, entries.ctypes.data, capacity,
+                                          byref(n), out.ctypes.data, n_out))
+        return entries[: n.value], out
 
     def minimize(self, theta0, **options):
         """L-BFGS inside the library (ad4cl_cuda_minimize_lbfgs) -> (theta, dict of the result fields)."""

@@ -183,6 +183,19 @@ int ad4cl_cuda_eval_device(ad4cl_kernel* kernel, const double* theta_dev, int np
 int ad4cl_cuda_check(ad4cl_kernel* kernel);
 int ad4cl_cuda_last_stats(ad4cl_kernel* kernel, ad4cl_eval_stats* stats);
 /*
+ * Tape export -- the debug / legacy path (what enqueueReadBuffer of the whole stack gave the
+ * reference's host, test/admb/simple.cpp:315).  Records the kernel WITHOUT sweeping and rewrites
+ * every work-item's tape as the reference's 40-byte ad_entry records (ad.cl:75-79), in work-item
+ * order, into entries_out (capacity entries; *n_entries receives the count).  out_vars (n_out
+ * 16-byte ad_variables, may be NULL) receives out[i] with its id in the exported numbering:
+ * independents keep their ids, temporaries are numbered from first_free_id on.  Legacy host code can
+ * continue as in simple.cpp:357-369: gs->stack_current += n, gs->current_variable_id = first_free_id
+ * + n, host sum of out[], epilogue, compute_gradient.  Small problems only.
+ */
+int ad4cl_cuda_export_tape(ad4cl_kernel* kernel, const double* theta, int nparams, int first_free_id,
+        void* entries_out, long long capacity, long long* n_entries, void* out_vars, long long n_out);
+
+/*
  * Opt-in device timing of the fused record+sweep+reduce kernel ALONE (CUDA events
  * recorded on the launching stream around that one launch; the analogue of the
  * reference's CL_PROFILING event.getProfilingInfo, test/admb/simple.cpp:301-310).
