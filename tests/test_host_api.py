@@ -145,3 +145,28 @@ def test_benchmarks_txt_objective_value(ctx):
     k.free()
     assert abs(res["f"] - 8.8535e6) <= 2e-4 * 8.8535e6
     assert abs(theta[0] - 1.99987523364) < 5e-4 and abs(theta[1] - 4.02338318012) < 0.06   # dist/.../simple.par:1-5
+
+
+@pytest.mark.gpu
+def test_admb_style_example_writes_par(tmp_path):
+    """examples/simple_admb.py: simple.dat in, simple.par out (formats of test/admb/simple.dat and
+    test/admb/bin/simple.par), the kernel file named in the .dat JIT-built as simple.cpp:138-175 does."""
+    import importlib.util
+    import shutil
+    shutil.copy(os.path.join(REPO, "ad4cl_b200", "kernels", "objectives.cl"), tmp_path / "kernel.cl")
+    # the .dat names a kernel file with an entry called AD, like test/admb/simple.cl
+    text = open(tmp_path / "kernel.cl").read().replace("__kernel void linreg2_p(", "__kernel void AD(")
+    open(tmp_path / "kernel.cl", "w").write(text)
+    open(tmp_path / "simple.dat", "w").write(
+        "# number of observations\n     100003\n# gradient method 0 = admb, 1 = ad4cl_device, 2 = ad4cl_host\n     1\n"
+        "# ad4cl stack size\n     5000000\n#path to ad.cl\n     ../../ad.cl\n#path to kernel simple.cl\n     kernel.cl\n"
+        "#gpu index. for host with more than one gpu.(first is 0)\n     0\n")
+    spec = importlib.util.spec_from_file_location("simple_admb", os.path.join(REPO, "examples", "simple_admb.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    theta, res = mod.main(str(tmp_path / "simple.dat"), str(tmp_path))
+    par = open(tmp_path / "simple.par").read().splitlines()
+    assert par[0].startswith("# Number of parameters = 2  Objective function value = ")
+    assert par[1] == "# a:" and par[3] == "# b:"
+    assert abs(float(par[2]) - 2.0) < 0.01 and abs(float(par[4]) - 4.0) < 0.2      # bin/simple.par: 1.9997, 4.0251
+    assert abs(res["f"] - 770466.0) <= 1e-3 * 770466.0                              # bin/simple.par:1 (N = 100 003)
