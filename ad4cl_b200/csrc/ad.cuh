@@ -358,7 +358,9 @@ AD4CL_DEV struct ad_variable ad_commit_p(struct ad_gradient_structure* gs,
     struct ad_variable ret = {out.value, 0};
     if (gs->recording != 1) return ret;
     double g[PRIVATE_GRADIENT_SIZE];
-    for (int i = 0; i < PRIVATE_GRADIENT_SIZE; i++) g[i] = 0.0;
+    int used = pgs->current_ad_variable_id + pgs->counter; /* ids the private stack can refer to */
+    if (used > PRIVATE_GRADIENT_SIZE) used = PRIVATE_GRADIENT_SIZE;
+    for (int i = 0; i < used; i++) g[i] = 0.0;
     ad_gradient_p(pgs, out, g);
     const int nparams = gs->current_ad_variable_id;
     int have = 0;

@@ -31,6 +31,9 @@ AD4CL_OBJECTIVE_ENTRY(linreg2_g,
 AD4CL_OBJECTIVE_ENTRY(linreg2_p,
     (const struct ad_variable* a, const struct ad_variable* b, double* x, double* y, int size),
     (gs, gradient_stack, a, b, x, y, out, size))
+AD4CL_OBJECTIVE_ENTRY(linreg2_private,
+    (const struct ad_variable* a, const struct ad_variable* b, double* x, double* y, int size),
+    (gs, gradient_stack, a, b, x, y, out, size))
 AD4CL_OBJECTIVE_ENTRY(linreg2_var,
     (struct ad_variable* a, struct ad_variable* b, double* x, double* y, int size),
     (gs, gradient_stack, a, b, x, y, out, size))
@@ -55,6 +58,7 @@ AD4CL_OBJECTIVE_ENTRY(matrix_elementwise,
 extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(linreg2_g, "GSVVDDOi"),
     ROW(linreg2_p, "GSVVDDOi"),
+    ROW(linreg2_private, "GSVVDDOi"),
     ROW(linreg2_var, "GSVVDDOi"),
     ROW(regression_logistic_var, "GSVDDOiii"),
     ROW(regression_linear, "GSVDDOiii"),

@@ -312,6 +312,28 @@ __kernel void op_zoo_pad(__global struct ad_gradient_structure* gs,
 }
 #endif
 
+/* config 1 on a PRIVATE stack: the 4 operators stay in registers / local memory and only the two
+ * pre-accumulated partials d(out)/da, d(out)/db reach the thread tape (3 slots instead of 6) */
+#ifdef AD4CL_HAVE_COMMIT_P
+__kernel void linreg2_private(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __constant struct ad_variable* a,
+        __constant struct ad_variable* b,
+        __global double* x,
+        __global double* y,
+        __global struct ad_variable* out, int size) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_private_gradient_structure p;
+        ad_init_p(&p);
+        p.current_ad_variable_id = gs->current_ad_variable_id;
+        struct ad_variable res = ad_minus_vd_p(&p, ad_plus_p(&p, ad_times_vd_p(&p, *a, x[id]), *b), y[id]);
+        out[id] = ad_commit_p(gs, &p, ad_times_p(&p, res, res));
+    }
+}
+#endif
+
 /* the same chain on a PRIVATE stack (ad.cl:1216-1829), pre-accumulated into the thread
  * tape with ad_commit_p: only 3 slots per work-item leave the registers / local memory */
 #ifdef AD4CL_HAVE_COMMIT_P

@@ -53,9 +53,13 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
 
 def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 33, p: int = 10) -> Workload:
     start, count = shard_range(n, rank, world)
-    if name in ("linreg2_main", "linreg2_simple"):
+    if name in ("linreg2_main", "linreg2_simple", "linreg2_private"):
         gen = synth.main_cpp_recipe if name == "linreg2_main" else synth.simple_cpp_recipe
         x, y, (a, b) = gen(n, start, count)
+        if name == "linreg2_private":   # the 4 operators on a private stack, 2 pre-accumulated operators on the tape
+            return Workload(name, "linreg2_private", np.array([a, b]), x, y, count, epilogue="half_n_log",
+                            epilogue_n=n, max_ops=4, max_slots=6, ops_total=2 * count, slots_total=3 * count,
+                            input_bytes=16 * count, linreg2=True)
         return Workload(name, "linreg2_p", np.array([a, b]), x, y, count, epilogue="half_n_log", epilogue_n=n,
                         max_ops=4, max_slots=6, ops_total=4 * count, slots_total=6 * count,
                         input_bytes=16 * count, linreg2=True)

@@ -168,3 +168,17 @@ def test_var_kernel_through_the_jit(ctx):
     fb, gb = kb.eval(w.theta)
     kb.free()
     assert f == fb and np.array_equal(g, gb)
+
+
+def test_config1_on_a_private_stack(ctx, oracle_api):
+    """linreg2_private: simple.cl's four operators through the *_p family + ad_commit_p; same f and
+    gradient as the reference's evaluation of the pad-family kernel, 3 slots per work-item on the tape."""
+    w = W.describe("linreg2_private", 100003)
+    ref = oracle_api.best(False).eval_objective("linreg2_p", w.theta, w.d0, w.d1, w.size, epilogue=1, ops_per_item=4)
+    k = W.bind(ctx, w)
+    f, g = k.eval(w.theta)
+    st = k.stats()
+    k.free()
+    assert abs(f - ref["f"]) <= 1e-12 * abs(ref["f"])
+    assert np.max(np.abs(g - ref["grad"])) <= 1e-12 * np.max(np.abs(ref["grad"]))
+    assert int(st["slots"]) == 3 * w.size and int(st["ops"]) == 2 * w.size
