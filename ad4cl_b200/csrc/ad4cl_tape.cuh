@@ -252,9 +252,6 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
     }
 }
 
-#ifndef AD4CL_FAR_RED
-#define AD4CL_FAR_RED 0
-#endif
 #ifndef AD4CL_SWEEP_UNROLL
 #define AD4CL_SWEEP_UNROLL 4
 #endif

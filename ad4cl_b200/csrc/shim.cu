@@ -186,13 +186,11 @@ struct ad4cl_kernel {
     ad4cl::LaunchInfo L{};
     long long data_items = 0;
     struct ad_variable* params_dev = nullptr;
-    double* theta_dev = nullptr;
     double* partials = nullptr;
     double* result_dev = nullptr;
     double* global_grad = nullptr;
     int* status_dev = nullptr;
     char* arena = nullptr;
-    double* theta_pinned = nullptr;
     struct ad_variable* params_pinned = nullptr; /* host-packed {theta_i, id = i}: no pack kernel on the host path */
     double* result_pinned = nullptr;             /* nparams + 4 doubles: [grad, f, ops, slots, status] */
     int* status_pinned = nullptr;
@@ -216,15 +214,15 @@ struct ad4cl_kernel {
     }
 
     void release() {
-        cudaFree(params_dev); cudaFree(theta_dev); cudaFree(partials); cudaFree(result_dev);
+        cudaFree(params_dev); cudaFree(partials); cudaFree(result_dev);
         cudaFree(global_grad); cudaFree(status_dev); cudaFree(arena);
-        cudaFreeHost(theta_pinned); cudaFreeHost(result_pinned); cudaFreeHost(status_pinned);
+        cudaFreeHost(result_pinned); cudaFreeHost(status_pinned);
         cudaFreeHost(params_pinned);
         params_pinned = nullptr;
         drop_graphs();
-        params_dev = nullptr; theta_dev = nullptr; partials = nullptr; result_dev = nullptr;
+        params_dev = nullptr; partials = nullptr; result_dev = nullptr;
         global_grad = nullptr; status_dev = nullptr; arena = nullptr;
-        theta_pinned = nullptr; result_pinned = nullptr; status_pinned = nullptr;
+        result_pinned = nullptr; status_pinned = nullptr;
         ready = false;
     }
 };
@@ -329,7 +327,6 @@ int prepare(ad4cl_kernel* k, int nparams) {
     const int pcols = (acc == AD4CL_ACC_GLOBAL ? 0 : nparams) + 3; /* columns of the per-block partials */
 
     CUDA_TRY(cudaMalloc(&k->params_dev, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
-    CUDA_TRY(cudaMalloc(&k->theta_dev, sizeof (double) * (size_t) std::max(nparams, 1)));
     CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) grid * pcols));
     CUDA_TRY(cudaMalloc(&k->result_dev, sizeof (double) * (size_t) (ncols + 1)));
     CUDA_TRY(cudaMalloc(&k->status_dev, sizeof (int)));
@@ -344,7 +341,6 @@ int prepare(ad4cl_kernel* k, int nparams) {
         }
         CUDA_TRY(cudaMemset(k->arena, 0, arena_bytes)); /* far bitmaps must start clear */
     }
-    CUDA_TRY(cudaMallocHost(&k->theta_pinned, sizeof (double) * (size_t) std::max(nparams, 1)));
     CUDA_TRY(cudaMallocHost(&k->result_pinned, sizeof (double) * (size_t) (ncols + 1)));
     CUDA_TRY(cudaMallocHost(&k->params_pinned, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
     memset(k->params_pinned, 0, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1));
