@@ -22,4 +22,11 @@ def test_bounds_checked_build_runs_every_path_clean():
     env = dict(os.environ, AD4CL_CUDA_LIB=dbg)
     checked = subprocess.run([sys.executable, prog], capture_output=True, text=True, timeout=300, env=env)
     assert checked.returncode == 0, checked.stderr[-2000:]      # a failed bounds check raises Ad4clError
-    assert checked.stdout == plain.stdout
+    import re
+    num = re.compile(r"-?\d+\.\d+(?:e[-+]?\d+)?")
+    a, b = plain.stdout.splitlines(), checked.stdout.splitlines()
+    assert len(a) == len(b) > 10
+    for la, lb in zip(a, b):
+        assert num.sub("#", la) == num.sub("#", lb)
+        for x, y in zip(num.findall(la), num.findall(lb)):      # fp64 atomics (acc = global) are not order-deterministic
+            assert abs(float(x) - float(y)) <= 1e-12 * max(1.0, abs(float(x)))
