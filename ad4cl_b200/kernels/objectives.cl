@@ -111,7 +111,9 @@ __kernel void regression_logistic(__global struct ad_gradient_structure* gs,
  *   i1   : global index of this shard's first replicate (0 on one GPU): a multi-GPU
  *          run gives every rank a slice of the replicates of EVERY cell, so all
  *          shards have the same mix of tape lengths
- *   fleet of a replicate = (rep / 32) % 6  (fleets cycle over blocks of 32 replicates)
+ *   d1   : d1[0] = R_global, the replicates per cell of the WHOLE problem
+ *   fleet of a replicate = rep*6/R_global  (6 contiguous blocks of replicates: the fleet
+ *          deviation's parameter id is warp-uniform except at the 5 block boundaries)
  * Baranov: Z = M + F_y s_a ; N = R_c exp(-sum_{k<a} Z_{y-a+k,k}) ;
  *          Chat = F s / Z (1 - exp(-Z)) N q ;
  *          out = (ln C - ln Chat)^2 / (2 sigma^2) + ln sigma
@@ -126,7 +128,6 @@ __kernel void regression_logistic(__global struct ad_gradient_structure* gs,
 #define CAA_LOGSIGMA 93
 #define CAA_FLEETDEV 94
 #define CAA_FLEETS 6
-#define CAA_FLEET_BLOCK 32
 
 __kernel void catch_at_age(__global struct ad_gradient_structure* gs,
         __global struct ad_entry* gradient_stack,
@@ -142,7 +143,7 @@ __kernel void catch_at_age(__global struct ad_gradient_structure* gs,
         const int year = cell % CAA_YEARS;
         const int age = cell / CAA_YEARS;
         const int cohort = year - age + (CAA_AGES - 1);
-        const int fleet = (rep / CAA_FLEET_BLOCK) % CAA_FLEETS;
+        const int fleet = (int) (((long long) rep * CAA_FLEETS) / (long long) d1[0]);
 
         struct ad_variable M = ad_exp(gs, theta[CAA_LOGM]);
         struct ad_variable Z = M;

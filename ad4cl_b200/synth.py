@@ -147,9 +147,6 @@ def caa_log_chat_table(theta: np.ndarray) -> np.ndarray:
     return tab
 
 
-CAA_FLEET_BLOCK = 32   # fleets cycle over blocks of 32 replicates: fleet = (rep // 32) % 6
-
-
 def catch_at_age(n: int, rep0: int = 0, nrep: int | None = None):
     """Observed log catch for the replicate slice [rep0, rep0 + nrep) of an n-observation problem
     (n = 400 R): observation (cell, rep) with cell = year + 40 age has the global index
@@ -165,7 +162,7 @@ def catch_at_age(n: int, rep0: int = 0, nrep: int | None = None):
     rep = rep0 + np.tile(np.arange(nrep, dtype=np.int64), CAA_YEARS * CAA_AGES)
     year = cell % CAA_YEARS
     age = cell // CAA_YEARS
-    fleet = (rep // CAA_FLEET_BLOCK) % CAA_FLEETS
+    fleet = (rep * CAA_FLEETS) // R      # 6 contiguous blocks of replicates
     obs = tab[fleet, age, year] + 0.3 * normal_at(4, rep + R * cell)
     theta0 = th_true + 0.02 * normal(5, 0, CAA_P)
     return obs, theta0, R

@@ -79,7 +79,7 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
         rep0, nrep = shard_range(R, rank, world)
         obs, theta0, _ = synth.catch_at_age(n, rep0, nrep)
         ops, slots = caa_totals(nrep)
-        return Workload(name, name, theta0, obs, None, len(obs), i0=nrep, i1=rep0, max_ops=128, max_slots=176,
+        return Workload(name, name, theta0, obs, np.array([float(R)]), len(obs), i0=nrep, i1=rep0, max_ops=128, max_slots=176,
                         ops_total=ops, slots_total=slots, input_bytes=8 * len(obs))
     if name == "tape_stress":
         x, theta = synth.tape_stress(n, start, count)

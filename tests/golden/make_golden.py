@@ -61,9 +61,9 @@ def cases():
     X, y, beta = synth.regression(3001, 10, "logistic")
     out["regression_logistic_3001"] = ("regression_logistic", beta, X, y, 3001, 10, 0, 3001, 0, 24)
     obs, th, R = synth.catch_at_age(80000)          # R = 200 replicates per cell: all six fleets occur
-    out["catch_at_age_80000"] = ("catch_at_age", th, obs, None, 80000, R, 0, 80000, 0, 130)
+    out["catch_at_age_80000"] = ("catch_at_age", th, obs, np.array([float(R)]), 80000, R, 0, 80000, 0, 130)
     obs, th, R = synth.catch_at_age(80000, 64, 72)  # a replicate slice, as a multi-GPU rank holds it
-    out["catch_at_age_slice"] = ("catch_at_age", th, obs, None, 400 * 72, 72, 64, 400 * 72, 0, 130)
+    out["catch_at_age_slice"] = ("catch_at_age", th, obs, np.array([float(R)]), 400 * 72, 72, 64, 400 * 72, 0, 130)
     for steps in (33, 200):
         x, th = synth.tape_stress(777)
         out[f"tape_stress_{steps}"] = ("tape_stress", th, x, None, 777, steps, 10, 777, 0, 3 * steps + 1)

@@ -64,7 +64,7 @@ def test_catch_at_age_full_size_against_oracle_on_a_replicate_slice(ctx, oracle_
     10^7-observation problem (every (year, age) cell, 50 replicates): same inputs, same kernel."""
     n = 10_000_000
     obs, theta0, R = synth.catch_at_age(n, 12345, 50)
-    ref = oracle_api.best(False).eval_objective("catch_at_age", theta0, obs, None, len(obs), 50, 12345, ops_per_item=130)
+    ref = oracle_api.best(False).eval_objective("catch_at_age", theta0, obs, np.array([float(R)]), len(obs), 50, 12345, ops_per_item=130)
     w = W.describe("catch_at_age", n)
     w.d0, w.size, w.i0, w.i1 = obs, len(obs), 50, 12345
     k = W.bind(ctx, w)

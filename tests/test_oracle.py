@@ -165,10 +165,10 @@ def test_fixed_gradient_is_the_true_gradient(oracle_api):
     n = 40000
     obs, th, R = synth.catch_at_age(n)
     port = oracle_api.Port(False)
-    g = port.eval_objective("catch_at_age", th, obs, None, n, R, 0, ops_per_item=130)["grad"]
+    g = port.eval_objective("catch_at_age", th, obs, np.array([float(R)]), n, R, 0, ops_per_item=130)["grad"]
     for k in (0, 50, 89, 90, 91, 92, 93, 94, 96):
         e = np.zeros(100)
         e[k] = 1e-6
-        fp = port.eval_objective("catch_at_age", th + e, obs, None, n, R, 0, ops_per_item=130)["f"]
-        fm = port.eval_objective("catch_at_age", th - e, obs, None, n, R, 0, ops_per_item=130)["f"]
+        fp = port.eval_objective("catch_at_age", th + e, obs, np.array([float(R)]), n, R, 0, ops_per_item=130)["f"]
+        fm = port.eval_objective("catch_at_age", th - e, obs, np.array([float(R)]), n, R, 0, ops_per_item=130)["f"]
         assert abs((fp - fm) / 2e-6 - g[k]) <= 1e-6 * max(1.0, abs(g[k]))
