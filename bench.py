@@ -352,9 +352,13 @@ def main():
                            l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
                            tape_tier=args.tape, acc_mode=args.acc),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P, "d2h_bytes_per_step": 8 * (P + 3) + 4,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    # N = 1: ad4cl_cuda_eval moves P host-packed ad_variables (16 B each) up and P+4 doubles down;
+                    # N > 1: P doubles up, the all-reduced P+3 doubles down
+                    "h2d_bytes_per_step": 16 * P if world == 1 else 8 * P,
+                    "d2h_bytes_per_step": 8 * (P + 4) if world == 1 else 8 * (P + 3),
                     "note": "observations device-resident across evaluations as in simple.cpp:206-230; "
-                            "theta up / [grad,f,ops,slots]+status down every step"},
+                            "theta up / [grad,f,ops,slots(,status)] down every step"},
             "gpu_launches": (4 if comm is not None else 3) * K, "clocks": clocks, "roofline": roofline,
             "ad_ops_per_s": float(st_result[P + 1]) * value,
             "objective": float(st_result[P])}
