@@ -143,7 +143,7 @@ __kernel void catch_at_age(__global struct ad_gradient_structure* gs,
         const int year = cell % CAA_YEARS;
         const int age = cell / CAA_YEARS;
         const int cohort = year - age + (CAA_AGES - 1);
-        const int fleet = (int) (((long long) rep * CAA_FLEETS) / (long long) d1[0]);
+        const int fleet = (int) (((long) rep * CAA_FLEETS) / (long) d1[0]); /* `long` is 64-bit in OpenCL C, CUDA and LP64 C */
 
         struct ad_variable M = ad_exp(gs, theta[CAA_LOGM]);
         struct ad_variable Z = M;

@@ -154,6 +154,37 @@ def cpu_eval_rate(workload: str, n_full: int, budget_s: float, steps: int = 1, w
     return rate_full, info
 
 
+def opencl_reference_rate(workload: str, n_full: int, n_sample: int):
+    """Context for the CPU baseline: the reference's UNMODIFIED OpenCL path -- ad.cl + the
+    kernel text built by the OpenCL platform of this very GPU, the simple.cpp launch / whole-stack read-back
+    protocol, the ad4cl.h host sum and serial sweep -- on a bounded sample, when the box has an OpenCL GPU
+    platform.  Part of the baseline leg: the only other place bench.py touches oracle/."""
+    try:
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import opencl_ref
+        from ad4cl_b200 import workloads as W
+        if not opencl_ref.available():
+            return {"unavailable": "no OpenCL GPU platform on this box or oracle/_ref/cl not built"}
+        ocl = opencl_ref.OpenCLReference(True)
+        w = W.describe(workload, n_sample)
+        epi = 1 if w.epilogue == "half_n_log" else 0
+        best = None
+        for _ in range(2):      # first call builds the program
+            r = ocl.eval_objective(w.kernel, w.theta, w.d0, w.d1, w.size, w.i0, w.i1, epilogue=epi, ops_per_item=w.max_ops)
+            if best is None or r["total_ms"] < best["total_ms"]:
+                best = r
+        scale = n_full / n_sample
+        return {"value": 1e3 / (best["total_ms"] * scale), "unit": UNIT, "device": ocl.device_name, "n_sample": n_sample,
+                "kernel_ms": best["kernel_ms"], "readback_ms": best["readback_ms"], "host_sum_and_sweep_ms": best["host_ms"],
+                "total_ms": best["total_ms"], "readback_bytes": best["readback_bytes"],
+                "kernel_only_evals_per_s": 1e3 / (best["kernel_ms"] * scale),
+                "note": "unmodified ad.cl on NVIDIA's OpenCL platform, local 64; recording kernel on the GPU, then the "
+                        "reference protocol reads the whole 40 B/entry stack back and sweeps it on ONE host thread; "
+                        f"scaled linearly to {n_full} observations"}
+    except Exception as e:  # noqa: BLE001 -- context only, never fails the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -365,6 +396,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, info = cpu_eval_rate(args.workload, n, budget_s=25.0)
+        info["opencl_on_this_gpu"] = opencl_reference_rate(args.workload, n, min(info["n_sample"], 1_000_000))
         line["cpu_baseline"] = info
     if comm is not None:
         comm.check()

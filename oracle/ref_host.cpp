@@ -82,6 +82,26 @@ extern "C" {
 int ref_sizeof_host_gs(void) { return (int) sizeof (host_gs_t); }
 
 /*
+ * The host half of the protocol on a stack that was recorded ELSEWHERE -- by the reference's
+ * unmodified OpenCL kernels on a real OpenCL device (oracle/opencl_ref.py) and read back with
+ * enqueueReadBuffer, exactly as simple.cpp:312-317 does: gpu_restore, host sum of out[], epilogue,
+ * compute_gradient.  `stack` must have room for counter + n + 2 entries.
+ */
+int ref_finish_stack(entry_t* stack, int counter, int nparams, var_t* out, int n, int epilogue,
+        double* f, double* grad, long long* entries, double* t_ms) {
+    host_gs_t gs_s;
+    host_gs_t* gs = &gs_s;
+    gs->gradient_stack = stack;
+    gs->current_variable_id = nparams;
+    gs->stack_current = 0;
+    gs->recording = 1;
+    gs->counter = counter;
+    gpu_restore(gs);
+    finish(gs, out, n, epilogue, nparams, f, grad, entries, t_ms);
+    return 0;
+}
+
+/*
  * Config 1 through the reference's own kernels.
  *   variant 0: kernel.cl   1: test/admb/simple.cl   2: host twin AD()
  *   (simple.cpp:14-28, host ops of ad4cl.h -- the AD4CL_HOST method)

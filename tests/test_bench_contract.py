@@ -51,5 +51,7 @@ def test_gpu_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 1600 and d["e2e"]["d2h_bytes_per_step"] == 832
     assert 0.5 * d["value"] < d["e2e"]["value"] <= 1.05 * d["value"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] < d["value"] / 100
+    ocl = d["cpu_baseline"]["opencl_on_this_gpu"]            # context: the unmodified OpenCL path on this GPU, if it has one
+    assert "unavailable" in ocl or 0 < ocl["value"] < d["value"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-9 * d["value"]
