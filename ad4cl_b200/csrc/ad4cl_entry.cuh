@@ -78,8 +78,9 @@ extern __shared__ __align__(16) unsigned char ad4cl_dyn_smem[];
 
 /*
  * Dynamic shared memory layout (doubles unless noted), B = blockDim.x, NW = B/32:
- *   ring      [window][B]           re-used as the block reduction scratch red[NW][ncols] after the
- *                                   last work-item (the region is max(window*B, NW*ncols) doubles)
+ *   ring      [B][window + 1]       thread-major, padded by one entry so that the lanes of a warp fall on
+ *                                   distinct banks; re-used as the block reduction scratch red[NW][ncols]
+ *                                   after the last work-item (the region is max((window+1)*B, NW*ncols) doubles)
  *   thread_acc[nparams][B]          kAccThread only
  *   warp_acc  [NW][nparams]         kAccWarp only
  *   tape rows [NW][smem_region]     tape_in_smem only (bytes)
@@ -88,7 +89,7 @@ __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int w
         bool tape_in_smem, unsigned cap_slots, bool far) {
     const int nw = block / 32;
     const size_t red = (size_t) nw * ((acc_mode == kAccGlobal ? 0 : nparams) + 3);
-    size_t d = (size_t) window * block;
+    size_t d = (size_t) (window + 1) * block;
     if (d < red) d = red;
     if (acc_mode == kAccThread) d += (size_t) nparams * block;
     if (acc_mode == kAccWarp) d += (size_t) nw * nparams;
@@ -112,14 +113,14 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     double* smem = reinterpret_cast<double*> (ad4cl_dyn_smem);
     double* ring = smem;
     double* red = smem; /* the ring is dead (all zero) once the last work-item has been swept */
-    size_t shared_region = (size_t) L.window * B;
+    size_t shared_region = (size_t) (L.window + 1) * B;
     if (shared_region < (size_t) nw * ncols) shared_region = (size_t) nw * ncols;
     double* thread_acc = ring + shared_region;
     double* warp_acc = thread_acc + (MODE == kAccThread ? (size_t) P * B : 0);
     size_t dbl_bytes = (size_t) ((warp_acc + (MODE == kAccWarp ? (size_t) nw * P : 0)) - smem) * sizeof (double);
     dbl_bytes = (dbl_bytes + 127) & ~(size_t) 127;
 
-    for (int i = tid; i < L.window * B; i += B) ring[i] = 0.0;
+    for (int i = tid; i < (L.window + 1) * B; i += B) ring[i] = 0.0;
     if (MODE == kAccThread)
         for (int i = tid; i < P * B; i += B) thread_acc[i] = 0.0;
     if (MODE == kAccWarp)
@@ -142,7 +143,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     tape_bind(tape, region, L.cap_slots, P, L.window, L.use_far != 0);
 
     SweepTarget T;
-    T.ring = smem_u32(ring + tid);
+    T.ring = smem_u32(ring + (size_t) tid * (L.window + 1));
     T.stride = (unsigned) B * 8u;
     T.thread_acc = smem_u32(thread_acc + tid);
     T.warp_acc = smem_u32(warp_acc + (size_t) warp * P);

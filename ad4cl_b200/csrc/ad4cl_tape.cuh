@@ -75,7 +75,7 @@ enum Status : int {
 struct ThreadTape {
     char* cur;            /* address of this lane's partial in the next free row */
     char* begin;          /* row 0 */
-    char* end;            /* begin + capacity; kGuardRows guard rows follow */
+    int cap_id;           /* first_temp + capacity in slots; kGuardRows guard rows follow the column */
     int id_off;           /* byte offset from a row's partial to its id word, this lane */
     int next_id;          /* first_temp + index of the next free row */
     int first_temp;       /* number of independents: ids >= first_temp are tape positions */
@@ -102,7 +102,7 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
     const int lane = threadIdx.x & 31;
     t.begin = warp_region + lane * 8;
     t.cur = t.begin;
-    t.end = t.begin + (size_t) cap_slots * kRowBytes;
+    t.cap_id = first_temp + (int) cap_slots;
     t.id_off = kRowIdOffset - lane * 4;
     t.next_id = first_temp;
     t.first_temp = first_temp;
@@ -120,13 +120,25 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
 /* An operand W or more slots old cannot use the ring: mark the END slot of the
    operator that produced it.  The far plane is all zeros between work-items
    (the sweep restores it), so nothing has to be cleared here, and the OR needs
-   no return value: it is issued as a fire-and-forget reduction. */
-__device__ __forceinline__ int tape_note_far(ThreadTape* t, int pos) {
-    if (t->far_adj == nullptr) return kErrWindow;
-#if AD4CL_DEBUG_BOUNDS
-    if (pos < 0 || pos >= t->next_id - t->first_temp) return kErrBounds;
+   no return value: it is issued as a fire-and-forget reduction.  Rare, so it is
+   kept OUT of line and takes its inputs by value (the tape cursor stays in
+   registers): ~50 push sites per objective would otherwise each carry a copy,
+   and the entry's code footprint decides its instruction-cache behaviour. */
+#ifndef AD4CL_FAR_NOTE_INLINE
+#define AD4CL_FAR_NOTE_INLINE 0
 #endif
-    atomicOr(reinterpret_cast<int*> (t->begin + (size_t) pos * kRowBytes + t->id_off), kHasFarFlag);
+#if AD4CL_FAR_NOTE_INLINE
+__device__ __forceinline__
+#else
+static __device__ __noinline__
+#endif
+int tape_note_far(char* begin, int id_off, const char* far_adj, int pos, int nslots) {
+    if (far_adj == nullptr) return kErrWindow;
+#if AD4CL_DEBUG_BOUNDS
+    if (pos < 0 || pos >= nslots) return kErrBounds;
+#endif
+    (void) nslots;
+    atomicOr(reinterpret_cast<int*> (begin + (size_t) pos * kRowBytes + id_off), kHasFarFlag);
     return kOk;
 }
 
@@ -136,17 +148,14 @@ __device__ __forceinline__ int tape_note_far(ThreadTape* t, int pos) {
    (guard rows absorb the last operator of an overflowing tape); capacity is
    checked once per operator in tape_close_op. */
 __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
-    int word;
-    if (id < t->first_temp) {
-        word = id | kParamFlag | flags;
-    } else {
-        const int pos = id - t->first_temp;
-        word = pos | flags;
-        /* the operator being recorded ends at this row or the next one */
-        if (id + t->wm1 <= t->next_id && !(flags & kNopFlag)) {
-            t->status |= tape_note_far(t, pos);
-            word |= kFarFlag;
-        }
+    const int pos = id - t->first_temp;
+    /* pos < 0: an independent.  Otherwise a temporary; the operator being recorded ends at
+       this row or the next one, so the operand is out of the ring's reach when
+       id + (W - 1) <= next_id. */
+    int word = (pos < 0 ? (id | kParamFlag) : pos) | flags;
+    if (pos >= 0 && id + t->wm1 <= t->next_id && !(flags & kNopFlag)) {
+        word |= kFarFlag;
+        t->status |= tape_note_far(t->begin, t->id_off, t->far_adj, pos, t->next_id - t->first_temp);
     }
 #if AD4CL_DEBUG_BOUNDS
     if (t->cur < t->begin || t->cur >= t->begin + (size_t) t->cap_rows * kRowBytes
@@ -162,13 +171,16 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
 }
 
 /* Close the operator whose `k` slots were just pushed; returns its result id
-   (the position of its END slot). */
+   (the position of its END slot).  An operator that does not fit sets the sticky
+   overflow bit and restarts the column at row 0: every later access stays inside
+   this thread's own column, the sweep of the work-item is skipped
+   (ad4cl_entry.cuh) and the host reports the error. */
 __device__ __forceinline__ int tape_close_op(ThreadTape* t, int k) {
-    if (t->cur > t->end) { /* does not fit: drop the operator, keep the pointer inside the guard */
+    (void) k;
+    if (t->next_id > t->cap_id) {
         t->status |= kErrTapeOverflow;
-        t->cur -= k * kRowBytes;
-        t->next_id -= k;
-        return t->next_id;
+        t->cur = t->begin;
+        t->next_id = t->first_temp;
     }
     t->nops++;
     return t->next_id - 1;
@@ -217,8 +229,9 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
 }
 
 struct SweepTarget {
-    unsigned ring;        /* shared address of this thread's ring column; entry r at ring + r * stride */
-    unsigned stride;      /* bytes between consecutive entries of a column (block size * 8) */
+    unsigned ring;        /* shared address of this thread's ring: W + 1 doubles per thread (the pad keeps
+                             the lanes of a warp on distinct banks), entry r at ring + 8 r */
+    unsigned stride;      /* kAccThread: bytes between consecutive parameters of a column (block size * 8) */
     unsigned thread_acc;  /* kAccThread: shared address of this thread's column, parameter p at + p * stride */
     unsigned warp_acc;    /* kAccWarp: shared address of this warp's row of P accumulators */
     double* global_acc;   /* kAccGlobal: gradient array indexed by id */
@@ -233,19 +246,21 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
         }
     } else if (MODE == kAccWarp) {
         /* all 32 lanes arrive here together; group lanes by parameter id in
-           lowest-lane-first order so the summation order is fixed */
-        unsigned pending = __ballot_sync(0xffffffffu, is_param);
-        while (pending) {
-            const int leader = __ffs(pending) - 1;
-            const int lid = __shfl_sync(0xffffffffu, id, leader);
-            const bool mine = is_param && id == lid;
-            const unsigned members = __ballot_sync(0xffffffffu, mine);
-            const double v = warp_sum(mine ? c : 0.0);
-            if ((threadIdx.x & 31) == 0) {
+           lowest-lane-first order so the summation order is fixed.  Every lane holds the
+           group's sum after the butterfly and every lane performs the same update of the
+           warp's accumulator (same address, same value: one shared-memory wavefront). */
+        if (__any_sync(0xffffffffu, is_param)) {
+            unsigned pending = __ballot_sync(0xffffffffu, is_param);
+            while (pending) {
+                const int leader = __ffs(pending) - 1;
+                const int lid = __shfl_sync(0xffffffffu, id, leader);
+                const bool mine = is_param && id == lid;
+                const unsigned members = __ballot_sync(0xffffffffu, mine);
+                const double v = warp_sum(mine ? c : 0.0);
                 const unsigned a = T.warp_acc + (unsigned) lid * 8u;
                 sts_f64(a, lds_f64(a) + v);
+                pending &= ~members;
             }
-            pending &= ~members;
         }
     } else {
         if (is_param) atomicAdd(&T.global_acc[id], c);
@@ -283,7 +298,7 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
     if (seed_pos >= 0 && seed_pos < rows) {
         /* rows recorded after `out` are dead; drop those that could alias the seed's ring entry */
         if (rows - seed_pos > wmask) rows = seed_pos + wmask;
-        sts_f64(T.ring + (unsigned) (seed_pos & wmask) * T.stride, 1.0);
+        sts_f64(T.ring + ((unsigned) (seed_pos & wmask) << 3), 1.0);
     }
     const char* cur = t.begin + (size_t) rows * kRowBytes;
 
@@ -337,7 +352,7 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
             const int idw = id_now[j];
             if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
                 const int me = idx - 1 - j;
-                const unsigned r = T.ring + (unsigned) (me & wmask) * T.stride;
+                const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
                 w = lds_f64(r);
                 sts_f64(r, 0.0);
                 if (idw & kHasFarFlag) {
@@ -370,7 +385,7 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
             }
 #endif
             if (cls == 0) {
-                const unsigned a = T.ring + (unsigned) (payload & wmask) * T.stride;
+                const unsigned a = T.ring + ((unsigned) (payload & wmask) << 3);
                 sts_f64(a, lds_f64(a) + c);
             } else if (cls == kFarFlag) {
                 if (far_adj != nullptr) *reinterpret_cast<double*> (far_adj + (size_t) payload * kFarRowBytes) += c;
