@@ -288,6 +288,7 @@ template <int MODE>
 __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T) {
     constexpr int U = kSweepUnroll;
     const int wmask = t.wm1;
+    const unsigned pad_off = (unsigned) (wmask + 1) << 3;
     const int id_off = t.id_off;
     char* const far_adj = t.far_adj;
     int rows = t.next_id - t.first_temp;
@@ -384,13 +385,18 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
                 return;
             }
 #endif
-            if (cls == 0) {
-                const unsigned a = T.ring + ((unsigned) (payload & wmask) << 3);
+            {   /* Branch-free scatter (a taken branch costs this loop more than the few instructions it
+                   skips): a recent temporary adds to its ring entry, with per-thread accumulators
+                   (kAccThread) an independent adds to its accumulator, and a slot of any other class
+                   adds to the pad entry of this thread's ring (index W), which nothing ever reads. */
+                unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
+                if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
                 sts_f64(a, lds_f64(a) + c);
-            } else if (cls == kFarFlag) {
+            }
+            if (cls == kFarFlag) {
                 if (far_adj != nullptr) *reinterpret_cast<double*> (far_adj + (size_t) payload * kFarRowBytes) += c;
             }
-            sweep_param<MODE>(T, cls == kParamFlag, payload, c);
+            if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {
