@@ -36,6 +36,7 @@ struct LaunchInfo {
     int window;             /* adjoint ring entries per thread (power of two) */
     int use_far;            /* far-adjoint plane present in the arena */
     int tape_in_smem;       /* 1: tape rows live in dynamic shared memory */
+    int sweep_prefetch;     /* 1: the sweep prefetches two batches ahead into L2 (ad4cl_tape.cuh) */
     unsigned cap_slots;     /* per-thread tape capacity (operand slots) */
     char* arena;            /* HBM arena: one warp region per resident warp */
     unsigned long long warp_region;  /* bytes per warp region */
@@ -182,7 +183,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
             continue;
         }
         /* a thread whose tape overflowed skips the sweep (the host reports the error) */
-        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) tape_sweep<MODE>(tape, outv.id, T);
+        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) tape_sweep<MODE>(tape, outv.id, T, L.sweep_prefetch != 0);
         tape_rewind(tape);
     }
 

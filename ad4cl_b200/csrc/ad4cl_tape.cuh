@@ -122,17 +122,10 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
    (the sweep restores it), so nothing has to be cleared here, and the OR needs
    no return value: it is issued as a fire-and-forget reduction.  Rare, so it is
    kept OUT of line and takes its inputs by value (the tape cursor stays in
-   registers): ~50 push sites per objective would otherwise each carry a copy,
-   and the entry's code footprint decides its instruction-cache behaviour. */
-#ifndef AD4CL_FAR_NOTE_INLINE
-#define AD4CL_FAR_NOTE_INLINE 0
-#endif
-#if AD4CL_FAR_NOTE_INLINE
-__device__ __forceinline__
-#else
-static __device__ __noinline__
-#endif
-int tape_note_far(char* begin, int id_off, const char* far_adj, int pos, int nslots) {
+   registers): ~50 push sites per objective would otherwise each carry a copy.
+   (A predicated `red` in inline PTX instead of the call was measured slower:
+   ptxas wraps it in a branch anyway.) */
+static __device__ __noinline__ int tape_note_far(char* begin, int id_off, const char* far_adj, int pos, int nslots) {
     if (far_adj == nullptr) return kErrWindow;
 #if AD4CL_DEBUG_BOUNDS
     if (pos < 0 || pos >= nslots) return kErrBounds;
@@ -237,6 +230,27 @@ struct SweepTarget {
     double* global_acc;   /* kAccGlobal: gradient array indexed by id */
 };
 
+/* kAccWarp: all 32 lanes arrive here together; lanes are grouped by parameter id in
+   lowest-lane-first order so the summation order is fixed.  Every lane holds the group's sum
+   after the butterfly and every lane performs the same update of the warp's accumulator (same
+   address, same value: one shared-memory wavefront).  Inlined at each use: an out-of-line copy
+   (call + return per contribution) was measured 5 % slower on catch-at-age. */
+__device__ __forceinline__
+void warp_param_reduce(unsigned warp_acc, bool is_param, int id, double c) {
+    /* precondition (checked by the caller with one vote): at least one lane has is_param */
+    unsigned pending = __ballot_sync(0xffffffffu, is_param);
+    do {
+        const int leader = __ffs(pending) - 1;
+        const int lid = __shfl_sync(0xffffffffu, id, leader);
+        const bool mine = is_param && id == lid;
+        const unsigned members = __ballot_sync(0xffffffffu, mine);
+        const double v = warp_sum(mine ? c : 0.0);
+        const unsigned a = warp_acc + (unsigned) lid * 8u;
+        sts_f64(a, lds_f64(a) + v);
+        pending &= ~members;
+    } while (pending);
+}
+
 template <int MODE>
 __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param, int id, double c) {
     if (MODE == kAccThread) {
@@ -245,32 +259,87 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
             sts_f64(a, lds_f64(a) + c);
         }
     } else if (MODE == kAccWarp) {
-        /* all 32 lanes arrive here together; group lanes by parameter id in
-           lowest-lane-first order so the summation order is fixed.  Every lane holds the
-           group's sum after the butterfly and every lane performs the same update of the
-           warp's accumulator (same address, same value: one shared-memory wavefront). */
-        if (__any_sync(0xffffffffu, is_param)) {
-            unsigned pending = __ballot_sync(0xffffffffu, is_param);
-            while (pending) {
-                const int leader = __ffs(pending) - 1;
-                const int lid = __shfl_sync(0xffffffffu, id, leader);
-                const bool mine = is_param && id == lid;
-                const unsigned members = __ballot_sync(0xffffffffu, mine);
-                const double v = warp_sum(mine ? c : 0.0);
-                const unsigned a = T.warp_acc + (unsigned) lid * 8u;
-                sts_f64(a, lds_f64(a) + v);
-                pending &= ~members;
-            }
-        }
+        if (__any_sync(0xffffffffu, is_param)) warp_param_reduce(T.warp_acc, is_param, id, c);
     } else {
         if (is_param) atomicAdd(&T.global_acc[id], c);
     }
 }
 
+/* The sweep loop exists in two bodies selected per batch by a warp vote -- with and without the
+   far-plane code -- when that pays: measured +4 % with per-thread accumulators (regression,
+   tape_stress: short bodies), -4 % with the warp-shuffle reduction inlined four times
+   (catch-at-age), where a single body is kept. */
+#ifndef AD4CL_SWEEP_TWO_BODIES
+#define AD4CL_SWEEP_TWO_BODIES(MODE) ((MODE) == kAccThread)
+#endif
 #ifndef AD4CL_SWEEP_UNROLL
 #define AD4CL_SWEEP_UNROLL 4
 #endif
 constexpr int kSweepUnroll = AD4CL_SWEEP_UNROLL; /* rows fetched per batch; two batches are in flight */
+
+/*
+ * One slot of the sweep.  FAR = false is the body for a batch in which no lane of the warp holds
+ * a FAR operand or a HAS_FAR result: it carries no far-plane code at all, so the common path has
+ * no branches to skip over it (a taken branch costs the sweep more than the instructions it
+ * skips).  Returns false on a failed bounds check (AD4CL_DEBUG_BOUNDS builds only).
+ */
+template <int MODE, bool FAR>
+__device__ __forceinline__ bool sweep_slot(ThreadTape& t, const SweepTarget& T, double& w, int idw, double dx,
+        int me, int wmask, unsigned pad_off, char* far_adj) {
+    if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
+        const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
+        w = lds_f64(r);
+        sts_f64(r, 0.0);
+    }
+    if (FAR && (idw & (kFarFlag | kHasFarFlag))) { /* rare: ONE test for both far cases, so the common path skips one block */
+        if (idw & kHasFarFlag) { /* (END slots only) contributions that came through the far plane */
+#if AD4CL_DEBUG_BOUNDS
+            if (far_adj == nullptr || me < 0 || me >= t.cap_rows || idw >= 0) {
+                t.status |= kErrBounds;
+                return false;
+            }
+#endif
+            double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
+            w += *fa;
+            *fa = 0.0;
+        }
+        if ((idw & kFarFlag) && far_adj != nullptr) {
+#if AD4CL_DEBUG_BOUNDS
+            if ((idw & kIdMask) >= me) {
+                t.status |= kErrBounds;
+                return false;
+            }
+#endif
+            *reinterpret_cast<double*> (far_adj + (size_t) (idw & kIdMask) * kFarRowBytes) += w * dx;
+        }
+    }
+    const int payload = idw & kIdMask;
+    const double c = w * dx;
+    const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
+#if AD4CL_DEBUG_BOUNDS
+    if ((cls == 0 || cls == kFarFlag) && (payload < 0 || payload >= me)) { /* operands precede their use */
+        t.status |= kErrBounds;
+        return false;
+    }
+    if (cls == kParamFlag && payload >= t.first_temp) {
+        t.status |= kErrBounds;
+        return false;
+    }
+    if (!FAR && (cls == kFarFlag || (idw < 0 && (idw & kHasFarFlag)))) { /* the batch vote let a far slot through */
+        t.status |= kErrBounds;
+        return false;
+    }
+#endif
+    {   /* Branch-free scatter: a recent temporary adds to its ring entry, with per-thread
+           accumulators (kAccThread) an independent adds to its accumulator, and a slot of any
+           other class adds to the pad entry of this thread's ring (index W), which nothing reads. */
+        unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
+        if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
+        sts_f64(a, lds_f64(a) + c);
+    }
+    if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
+    return true;
+}
 
 /*
  * Reverse sweep of the current work-item's tape, seeded with 1 at `out_id`.
@@ -282,10 +351,10 @@ constexpr int kSweepUnroll = AD4CL_SWEEP_UNROLL; /* rows fetched per batch; two 
  * neighbouring work-items normally have identical shape).  The stream is read
  * kSweepUnroll rows at a time, one batch ahead of the batch being processed,
  * so the L2/HBM latency of a row is overlapped with the adjoint arithmetic of
- * the previous ones.
+ * the previous ones; `prefetch` additionally pulls the batch after that into L2.
  */
 template <int MODE>
-__device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T) {
+__device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const SweepTarget& T, bool prefetch) {
     constexpr int U = kSweepUnroll;
     const int wmask = t.wm1;
     const unsigned pad_off = (unsigned) (wmask + 1) << 3;
@@ -341,6 +410,19 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
             }
             cur -= U * kRowBytes;
             --batches;
+            /* The batch just requested is consumed one iteration from now; when the kernel is
+               latency-bound that is less than an HBM round trip (ncu, catch-at-age: 20 % of all stall
+               samples sat on the first use of a fetched row).  With `prefetch` the batch AFTER the
+               next one is pulled into L2 now, without registers: the warp's stream is contiguous,
+               a batch is U * 384 B = 3 U cache lines, and lanes 0 .. 3U-1 each touch one of them
+               (generic prefetch: a no-op when the tape lives in shared memory).  It is a launch
+               option because it costs a bandwidth-bound sweep up to 5 % (tape_stress): the shim
+               times both settings on the first evaluation (LaunchInfo.sweep_prefetch). */
+            if (prefetch && batches >= 2 && id_off > kRowIdOffset - 4 * 3 * U) {
+                const int lane = (kRowIdOffset - id_off) >> 2;
+                const char* line = cur - lane * 8 - 2 * U * kRowBytes + lane * 128;
+                asm volatile("prefetch.L2 [%0];" : : "l"(line));
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < U; j++) {
@@ -348,55 +430,23 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
                 id_next[j] = kNopFlag;
             }
         }
+#if AD4CL_DEBUG_BOUNDS
+        if (fetch && cur < t.begin) {
+            t.status |= kErrBounds;
+            return;
+        }
+#endif
+        int flags = 0;
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int idw = id_now[j];
-            if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
-                const int me = idx - 1 - j;
-                const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
-                w = lds_f64(r);
-                sts_f64(r, 0.0);
-                if (idw & kHasFarFlag) {
-#if AD4CL_DEBUG_BOUNDS
-                    if (far_adj == nullptr || me < 0 || me >= t.cap_rows) {
-                        t.status |= kErrBounds;
-                        return;
-                    }
-#endif
-                    double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
-                    w += *fa;
-                    *fa = 0.0;
-                }
-            }
-            const int payload = idw & kIdMask;
-            const double c = w * dx_now[j];
-            const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
-#if AD4CL_DEBUG_BOUNDS
-            if ((cls == 0 || cls == kFarFlag) && (payload < 0 || payload >= idx - 1 - j)) { /* operands precede their use */
-                t.status |= kErrBounds;
-                return;
-            }
-            if (cls == kParamFlag && payload >= t.first_temp) {
-                t.status |= kErrBounds;
-                return;
-            }
-            if (fetch && cur < t.begin) {
-                t.status |= kErrBounds;
-                return;
-            }
-#endif
-            {   /* Branch-free scatter (a taken branch costs this loop more than the few instructions it
-                   skips): a recent temporary adds to its ring entry, with per-thread accumulators
-                   (kAccThread) an independent adds to its accumulator, and a slot of any other class
-                   adds to the pad entry of this thread's ring (index W), which nothing ever reads. */
-                unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
-                if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
-                sts_f64(a, lds_f64(a) + c);
-            }
-            if (cls == kFarFlag) {
-                if (far_adj != nullptr) *reinterpret_cast<double*> (far_adj + (size_t) payload * kFarRowBytes) += c;
-            }
-            if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
+        for (int j = 0; j < U; j++) flags |= id_now[j];
+        if (!AD4CL_SWEEP_TWO_BODIES(MODE) || __any_sync(0xffffffffu, (flags & (kFarFlag | kHasFarFlag)) != 0)) {
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (!sweep_slot<MODE, true>(t, T, w, id_now[j], dx_now[j], idx - 1 - j, wmask, pad_off, far_adj)) return;
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (!sweep_slot<MODE, false>(t, T, w, id_now[j], dx_now[j], idx - 1 - j, wmask, pad_off, far_adj)) return;
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {

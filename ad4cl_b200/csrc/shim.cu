@@ -197,6 +197,7 @@ struct ad4cl_kernel {
     /* the host evaluation path replayed as one CUDA graph: [0] objective only, [1] with gradient */
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     bool graph_disabled = false;
+    bool tune_pending = false;   /* AD4CL_PREFETCH_AUTO: decided by autotune_prefetch on the first gradient evaluation */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ad4cl_eval_stats stats{};
     /* opt-in timing of the fused kernel alone (ad4cl_cuda_kernel_profile) */
@@ -358,6 +359,9 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.window = window;
     L.use_far = far ? 1 : 0;
     L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
+    L.sweep_prefetch = c.sweep_prefetch == AD4CL_PREFETCH_ON ? 1 : 0;
+    k->tune_pending = c.sweep_prefetch == AD4CL_PREFETCH_AUTO && tier != AD4CL_TAPE_SHARED; /* a no-op on a shared-memory tape */
+    k->stats.sweep_prefetch = k->tune_pending ? -1 : L.sweep_prefetch;
     L.cap_slots = cap_slots;
     L.arena = k->arena;
     L.warp_region = region;
@@ -473,6 +477,40 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
                 k->status_dev, status_out);
     }
     CUDA_TRY(cudaGetLastError());
+    return AD4CL_OK;
+}
+
+/*
+ * AD4CL_PREFETCH_AUTO: time the evaluation (pack + fused kernel + second stage, CUDA events on the
+ * context's stream) with the sweep's L2 prefetch off and on, and keep the faster setting for this
+ * configuration.  Runs once, on the first gradient evaluation, before the CUDA graph is captured.
+ * An evaluation longer than 50 ms is tape streaming at HBM speed, where the prefetch was never
+ * measured to help: it stays off without a second run.  The choice cannot change a result bit.
+ */
+int autotune_prefetch(ad4cl_kernel* k, const double* theta_dev) {
+    k->tune_pending = false;
+    cudaStream_t st = k->ctx->stream;
+    float best[2] = {1e30f, 1e30f};
+    for (int round = 0; round < 2; round++) {
+        for (int pf = 0; pf < 2; pf++) {
+            k->L.sweep_prefetch = pf;
+            CUDA_TRY(cudaEventRecord(k->ev0, st));
+            int rc = enqueue(k, theta_dev, k->result_dev, 1, 0);
+            if (rc != AD4CL_OK) return rc;
+            CUDA_TRY(cudaEventRecord(k->ev1, st));
+            CUDA_TRY(cudaEventSynchronize(k->ev1));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, k->ev0, k->ev1));
+            if (round > 0 || pf > 0 || ms > 50.f) best[pf] = std::min(best[pf], ms); /* the very first run also warms up */
+            if (pf == 0 && ms > 50.f) {
+                round = 2;
+                break;
+            }
+        }
+    }
+    k->L.sweep_prefetch = best[1] < best[0] ? 1 : 0;
+    k->stats.sweep_prefetch = k->L.sweep_prefetch;
+    CUDA_TRY(cudaMemsetAsync(k->status_dev, 0, sizeof (int), st)); /* an error shows up again in the evaluation proper */
     return AD4CL_OK;
 }
 
@@ -897,6 +935,7 @@ int ad4cl_cuda_kernel_config_default(ad4cl_kernel_config* cfg) {
     cfg->acc_mode = AD4CL_ACC_AUTO;
     cfg->tape_tier = AD4CL_TAPE_AUTO;
     cfg->epilogue = AD4CL_EPILOGUE_SUM;
+    cfg->sweep_prefetch = AD4CL_PREFETCH_AUTO;
     return AD4CL_OK;
 }
 
@@ -918,6 +957,10 @@ int ad4cl_cuda_eval_device(ad4cl_kernel* k, const double* theta_dev, int nparams
     CUDA_TRY(cudaSetDevice(k->ctx->device));
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
+    if (k->tune_pending && want_gradient) {
+        rc = autotune_prefetch(k, theta_dev);
+        if (rc != AD4CL_OK) return rc;
+    }
     return enqueue(k, theta_dev, result_dev, want_gradient, apply_epilogue);
 }
 
@@ -953,6 +996,13 @@ int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f
     for (int p = 0; p < nparams; p++) { /* ad_init_var, ad4cl.h:90-93: {value, id = p} */
         k->params_pinned[p].value = theta[p];
         k->params_pinned[p].id = p;
+    }
+    if (k->tune_pending && want) {
+        if (nparams > 0)
+            CUDA_TRY(cudaMemcpyAsync(k->params_dev, k->params_pinned, sizeof (struct ad_variable) * (size_t) nparams,
+                    cudaMemcpyHostToDevice, st));
+        rc = autotune_prefetch(k, nullptr);
+        if (rc != AD4CL_OK) return rc;
     }
     /* Replay the whole evaluation as one CUDA graph (captured on first use; the launches'
        arguments are fixed until an argument or the configuration changes).  Profiling needs

@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--local-size", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--prefetch", default="auto", choices=["auto", "off", "on"],
+                    help="sweep L2 prefetch (auto: the library times both on the first evaluation)")
     ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
                     help="N > 1: the library's one-shot NVLink all-reduce (default) or torch.distributed NCCL")
     args = ap.parse_args()
@@ -263,6 +265,8 @@ def main():
         cfg["local_size"] = args.local_size
     if args.blocks_per_sm:
         cfg["blocks_per_sm"] = args.blocks_per_sm
+    if args.prefetch != "auto":
+        cfg["prefetch"] = args.prefetch
     k = W.bind(ctx, w, **cfg)
 
     theta_host = torch.from_numpy(np.ascontiguousarray(w.theta)).pin_memory()
@@ -382,7 +386,9 @@ def main():
             "config": dict(config, ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
                            l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
-                           tape_tier=args.tape, acc_mode=args.acc),
+                           tape_tier=args.tape, acc_mode=args.acc,
+                           sweep_prefetch={1: "on", 0: "off"}.get(stats.get("sweep_prefetch"), "undecided")
+                           + (" (auto-tuned on the first evaluation)" if args.prefetch == "auto" else "")),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     # N = 1: ad4cl_cuda_eval moves P host-packed ad_variables (16 B each) up and P+4 doubles down;
                     # N > 1: P doubles up, the all-reduced P+3 doubles down

@@ -72,6 +72,16 @@ enum {
     AD4CL_TAPE_SHARED = 1   /* rows in shared memory (short tapes) */
 };
 
+/* L2 prefetch of tape rows two batches ahead in the sweep.  Helps a latency-bound evaluation
+   (catch-at-age: +6 %), costs a bandwidth-bound one up to 5 % (tape_stress); results are
+   bit-identical either way.  AUTO times both settings on the first gradient evaluation of a
+   configured kernel (two to four extra evaluations, once) and keeps the faster. */
+enum {
+    AD4CL_PREFETCH_AUTO = -1,
+    AD4CL_PREFETCH_OFF = 0,
+    AD4CL_PREFETCH_ON = 1
+};
+
 /* scalar epilogue applied to S = sum_i out_i */
 enum {
     AD4CL_EPILOGUE_SUM = 0,      /* f = S */
@@ -91,6 +101,7 @@ typedef struct ad4cl_kernel_config {
     double epilogue_n;         /* n of the epilogue; 0 = number of data work-items */
     int blocks_per_sm;         /* persistent grid = SMs x this; 0 = occupancy maximum */
     int reference_quirks;      /* builtin kernels only: 1 = reference arithmetic as written */
+    int sweep_prefetch;        /* AD4CL_PREFETCH_*: L2 prefetch of tape rows in the sweep (never changes a result bit) */
 } ad4cl_kernel_config;
 
 typedef struct ad4cl_eval_stats {
@@ -100,6 +111,7 @@ typedef struct ad4cl_eval_stats {
     size_t smem_bytes;
     size_t arena_bytes;
     float kernel_ms;        /* device time of the last evaluation (both launches) */
+    int sweep_prefetch;     /* the setting in use: 0 off, 1 on, -1 not decided yet (AD4CL_PREFETCH_AUTO before the first gradient evaluation) */
 } ad4cl_eval_stats;
 
 int ad4cl_cuda_init(int device, ad4cl_context** ctx);
