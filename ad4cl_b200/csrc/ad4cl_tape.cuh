@@ -272,6 +272,10 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
 #ifndef AD4CL_SWEEP_TWO_BODIES
 #define AD4CL_SWEEP_TWO_BODIES(MODE) ((MODE) == kAccThread)
 #endif
+#ifndef AD4CL_PREFETCH_BATCHES
+#define AD4CL_PREFETCH_BATCHES 2
+#endif
+constexpr int kPrefetchBatches = AD4CL_PREFETCH_BATCHES; /* the prefetch runs this many batches below the one being fetched */
 #ifndef AD4CL_SWEEP_UNROLL
 #define AD4CL_SWEEP_UNROLL 4
 #endif
@@ -418,9 +422,9 @@ __device__ __forceinline__ void tape_sweep(ThreadTape& t, int out_id, const Swee
                (generic prefetch: a no-op when the tape lives in shared memory).  It is a launch
                option because it costs a bandwidth-bound sweep up to 5 % (tape_stress): the shim
                times both settings on the first evaluation (LaunchInfo.sweep_prefetch). */
-            if (prefetch && batches >= 2 && id_off > kRowIdOffset - 4 * 3 * U) {
+            if (prefetch && batches >= kPrefetchBatches && id_off > kRowIdOffset - 4 * 3 * U) {
                 const int lane = (kRowIdOffset - id_off) >> 2;
-                const char* line = cur - lane * 8 - 2 * U * kRowBytes + lane * 128;
+                const char* line = cur - lane * 8 - kPrefetchBatches * U * kRowBytes + lane * 128;
                 asm volatile("prefetch.L2 [%0];" : : "l"(line));
             }
         } else {
