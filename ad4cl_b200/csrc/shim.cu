@@ -488,8 +488,13 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
  * measured to help: it stays off without a second run.  The choice cannot change a result bit.
  */
 int autotune_prefetch(ad4cl_kernel* k, const double* theta_dev) {
-    k->tune_pending = false;
     cudaStream_t st = k->ctx->stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return AD4CL_OK; /* a caller-owned stream under graph capture cannot be timed: stay off, decide on a later call */
+    }
+    k->tune_pending = false;
     float best[2] = {1e30f, 1e30f};
     for (int round = 0; round < 2; round++) {
         for (int pf = 0; pf < 2; pf++) {
