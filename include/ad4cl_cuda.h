@@ -187,7 +187,10 @@ int ad4cl_cuda_eval(ad4cl_kernel* kernel, const double* theta, int nparams, doub
  * nparams+3 doubles [grad..., S_or_f, ops, slots].  With apply_epilogue = 0 the
  * raw sums are left (so partial results of several devices can be added before
  * the epilogue is applied).  Errors raised by the launch itself surface at the
- * next ad4cl_cuda_check().
+ * next ad4cl_cuda_check().  With sweep_prefetch = AD4CL_PREFETCH_AUTO the FIRST gradient
+ * evaluation of a configured kernel first runs two to four timed evaluations and
+ * synchronises the stream (not while the stream is being captured into a CUDA graph:
+ * then the prefetch stays off until a later, uncaptured call).
  */
 int ad4cl_cuda_eval_device(ad4cl_kernel* kernel, const double* theta_dev, int nparams,
         double* result_dev, int want_gradient, int apply_epilogue);
