@@ -400,6 +400,9 @@ def main():
     stats = k.stats()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "frac_of_nominal_8TBs": achieved / 8000.0,
+                # what actually crossed the HBM interface (ncu capture of the same launch) over this run's kernel time
+                "dram_GBps": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9,
+                "dram_frac": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9 / peak,
                 "input_stream": {"bytes": w.input_bytes, "GBps": w.input_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "frac": w.input_bytes / (kernel_ms * 1e-3) / 1e9 / peak}, "kernel": f"{w.kernel}__entry (fused record+sweep+block reduce)",
                 "kernel_ms": kernel_ms, "kernel_ms_by_rank": kernel_ms_by_rank, "kernel_launches_timed": kernel_launches,
