@@ -82,6 +82,18 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ad4cl_kernel_config)
     assert int(out[3]) == host.EvalStats.kernel_ms.offset
 
 
+def test_config_defaults():
+    """ad4cl_cuda_kernel_config_default is pure host code: the AUTO choices (accumulator, tape tier, sweep
+    prefetch) are the -1 of their enums and the far plane is on."""
+    from ad4cl_b200 import host
+    cfg = host.KernelConfig()
+    assert host.lib.ad4cl_cuda_kernel_config_default(ctypes.byref(cfg)) == 0
+    assert (cfg.acc_mode, cfg.tape_tier, cfg.sweep_prefetch) == (host.ACC["auto"], host.TAPE["auto"], host.PREFETCH["auto"])
+    assert cfg.far_plane == 1 and cfg.global_size[1] == 1 and cfg.max_ops > 0
+    assert host.lib.ad4cl_cuda_kernel_config_default(None) != 0
+    assert b"NULL" in host.lib.ad4cl_cuda_last_error()
+
+
 def test_workload_bookkeeping():
     from ad4cl_b200 import synth, workloads as W
     n = 8000
