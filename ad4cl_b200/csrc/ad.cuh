@@ -86,6 +86,7 @@ struct ad_private_gradient_structure {
     int stack_current;
     int recording;
     int counter;
+    int overflow;   /* more than PRIVATE_STACK_SIZE entries were recorded: the stack stopped at the limit */
 };
 
 #define AD4CL_DEV __device__ __forceinline__
@@ -104,6 +105,7 @@ AD4CL_DEV void ad_init(struct ad_gradient_structure* gs, struct ad_entry* gradie
 /* ad.cl:133-142 */
 AD4CL_DEV void ad_init_p(struct ad_private_gradient_structure* gs) {
     gs->nslots = 0;
+    gs->overflow = 0;
     gs->counter = 0;
     gs->current_ad_variable_id = 0;
     gs->recording = 1;
@@ -132,8 +134,8 @@ AD4CL_DEV void pad_init(int operations, struct ad_gradient_structure* pgs,
 AD4CL_DEV void ad_init_var_g(struct ad_gradient_structure* gs, struct ad_variable* var, double value) {
     var->value = value;
     if (gs->recording == 1) {
-        ad4cl::tape_push(gs->tape, 0.0, 0, ad4cl::kEndFlag | ad4cl::kNopFlag);
-        var->id = ad4cl::tape_close_op(gs->tape, 1);
+        ad4cl::tape_push<1>(gs->tape, 0.0, 0, ad4cl::kEndFlag | ad4cl::kNopFlag, ad4cl::kNoId);
+        var->id = ad4cl::tape_close_op(gs->tape);
         gs->counter++;
     } else {
         var->id = 0;
@@ -144,32 +146,46 @@ AD4CL_DEV void ad_init_var_g(struct ad_gradient_structure* gs, struct ad_variabl
 
 namespace ad4cl {
 
+/* UA / UB = +1 / -1: the partial is the compile-time constant +1.0 / -1.0 (a unit slot owns no cell
+   on the tape, ad4cl_tape.cuh); 0: a general partial.  The dx arguments always carry the value. */
+template <int UA>
 AD4CL_DEV int record1(struct ad_gradient_structure* gs, double dx, int id) {
-    tape_push(gs->tape, dx, id, kEndFlag);
-    const int r = tape_close_op(gs->tape, 1);
+    ThreadTape* t = gs->tape;
+    const int prev = t->next_id - 1; /* id of the previous operator's result */
+    tape_push<UA>(t, dx, id, kEndFlag, prev);
+    const int r = tape_close_op(t);
     gs->counter++;
     return r;
 }
 
+template <int UA, int UB>
 AD4CL_DEV int record2(struct ad_gradient_structure* gs, double dx0, int id0, double dx1, int id1) {
-    tape_push(gs->tape, dx0, id0, 0);
-    tape_push(gs->tape, dx1, id1, kEndFlag);
-    const int r = tape_close_op(gs->tape, 2);
+    ThreadTape* t = gs->tape;
+    const int prev = t->next_id - 1;
+    tape_push<UA>(t, dx0, id0, 0, prev);
+    tape_push<UB>(t, dx1, id1, kEndFlag, prev);
+    const int r = tape_close_op(t);
     gs->counter++;
     return r;
 }
 
-/* private family: result id = counter + current_ad_variable_id as in ad.cl:1220-1221 */
+/* private family: result id = counter + current_ad_variable_id as in ad.cl:1220-1221.  A stack that
+   is full stops recording and says so (ad_commit_p reports it) instead of pairing later results
+   with the wrong slots. */
+template <int UA>
 AD4CL_DEV int record1(struct ad_private_gradient_structure* gs, double dx, int id) {
     const int index = gs->counter++;
     if (gs->nslots < 2 * PRIVATE_STACK_SIZE) {
         gs->slot_dx[gs->nslots] = dx;
         gs->slot_id[gs->nslots] = id | kEndFlag;
+        gs->nslots++;
+    } else {
+        gs->overflow = 1;
     }
-    gs->nslots++;
     return index + gs->current_ad_variable_id;
 }
 
+template <int UA, int UB>
 AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int id0, double dx1, int id1) {
     const int index = gs->counter++;
     if (gs->nslots + 1 < 2 * PRIVATE_STACK_SIZE) {
@@ -177,8 +193,10 @@ AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int 
         gs->slot_id[gs->nslots] = id0;
         gs->slot_dx[gs->nslots + 1] = dx1;
         gs->slot_id[gs->nslots + 1] = id1 | kEndFlag;
+        gs->nslots += 2;
+    } else {
+        gs->overflow = 1;
     }
-    gs->nslots += 2;
     return index + gs->current_ad_variable_id;
 }
 
@@ -201,33 +219,33 @@ AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int 
 #define AD4CL_COS_VALUE cos(av)
 #endif
 
-#define AD4CL_OP_VV(GS_T, NAME, VAL, DA, DB)                                              \
+#define AD4CL_OP_VV(GS_T, NAME, VAL, DA, DB, UA, UB)                                            \
     AD4CL_DEV struct ad_variable NAME(GS_T* gs, const struct ad_variable a, const struct ad_variable b) { \
         const double av = a.value, bv = b.value;                                            \
         const double val = (VAL);                                                           \
         struct ad_variable ret = {val, 0};                                                  \
         (void) av; (void) bv;                                                               \
-        if (gs->recording == 1) ret.id = ad4cl::record2(gs, (DA), a.id, (DB), b.id);        \
+        if (gs->recording == 1) ret.id = ad4cl::record2<UA, UB>(gs, (DA), a.id, (DB), b.id); \
         return ret;                                                                         \
     }
 
-#define AD4CL_OP_VD(GS_T, NAME, VAL, DA)                                                  \
+#define AD4CL_OP_VD(GS_T, NAME, VAL, DA, UA)                                                \
     AD4CL_DEV struct ad_variable NAME(GS_T* gs, const struct ad_variable a, double bv) {   \
         const double av = a.value;                                                          \
         const double val = (VAL);                                                           \
         struct ad_variable ret = {val, 0};                                                  \
         (void) av;                                                                          \
-        if (gs->recording == 1) ret.id = ad4cl::record1(gs, (DA), a.id);                    \
+        if (gs->recording == 1) ret.id = ad4cl::record1<UA>(gs, (DA), a.id);                \
         return ret;                                                                         \
     }
 
-#define AD4CL_OP_DV(GS_T, NAME, VAL, DB)                                                  \
+#define AD4CL_OP_DV(GS_T, NAME, VAL, DB, UB)                                                \
     AD4CL_DEV struct ad_variable NAME(GS_T* gs, double av, const struct ad_variable b) {   \
         const double bv = b.value;                                                          \
         const double val = (VAL);                                                           \
         struct ad_variable ret = {val, 0};                                                  \
         (void) bv;                                                                          \
-        if (gs->recording == 1) ret.id = ad4cl::record1(gs, (DB), b.id);                    \
+        if (gs->recording == 1) ret.id = ad4cl::record1<UB>(gs, (DB), b.id);                \
         return ret;                                                                         \
     }
 
@@ -236,7 +254,7 @@ AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int 
         const double av = a.value;                                                          \
         const double val = (VAL);                                                           \
         struct ad_variable ret = {val, 0};                                                  \
-        if (gs->recording == 1) ret.id = ad4cl::record1(gs, (DA), a.id);                    \
+        if (gs->recording == 1) ret.id = ad4cl::record1<0>(gs, (DA), a.id);                 \
         return ret;                                                                         \
     }
 
@@ -244,11 +262,11 @@ AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int 
 #define AD4CL_OP_EQ(GS_T, NAME_V, NAME_D)                                                 \
     AD4CL_DEV void NAME_V(GS_T* gs, struct ad_variable* a, const struct ad_variable b) {   \
         a->value += b.value;                                                                \
-        if (gs->recording == 1) a->id = ad4cl::record2(gs, 1.0, a->id, 1.0, b.id);          \
+        if (gs->recording == 1) a->id = ad4cl::record2<1, 1>(gs, 1.0, a->id, 1.0, b.id);    \
     }                                                                                       \
     AD4CL_DEV void NAME_D(GS_T* gs, struct ad_variable* a, double b) {                     \
         a->value += b;                                                                      \
-        if (gs->recording == 1) a->id = ad4cl::record1(gs, 1.0, a->id);                     \
+        if (gs->recording == 1) a->id = ad4cl::record1<1>(gs, 1.0, a->id);                  \
     }
 
 /* Arithmetic rows.  Reference lines (global / pad / private):
@@ -260,19 +278,19 @@ AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int 
  *   inv = 1.0 / b ;  d/da = inv ;  d/db = -1.0 * result * inv.
  */
 #define AD4CL_ARITHMETIC(GS_T, PRE, SUF, TIMES_DV_DB)                                              \
-    AD4CL_OP_VV(GS_T, PRE##plus##SUF, av + bv, 1.0, 1.0)                                            \
-    AD4CL_OP_VD(GS_T, PRE##plus_vd##SUF, av + bv, 1.0)                                              \
-    AD4CL_OP_DV(GS_T, PRE##plus_dv##SUF, av + bv, 1.0)                                              \
+    AD4CL_OP_VV(GS_T, PRE##plus##SUF, av + bv, 1.0, 1.0, 1, 1)                                         \
+    AD4CL_OP_VD(GS_T, PRE##plus_vd##SUF, av + bv, 1.0, 1)                                            \
+    AD4CL_OP_DV(GS_T, PRE##plus_dv##SUF, av + bv, 1.0, 1)                                            \
     AD4CL_OP_EQ(GS_T, PRE##plus_eq##SUF, PRE##plus_eq_d##SUF)                                       \
-    AD4CL_OP_VV(GS_T, PRE##minus##SUF, av - bv, 1.0, -1.0)                                          \
-    AD4CL_OP_VD(GS_T, PRE##minus_vd##SUF, av - bv, 1.0)                                             \
-    AD4CL_OP_DV(GS_T, PRE##minus_dv##SUF, av - bv, -1.0)                                            \
-    AD4CL_OP_VV(GS_T, PRE##times##SUF, av * bv, AD4CL_TIMES_DA, AD4CL_TIMES_DB)                     \
-    AD4CL_OP_VD(GS_T, PRE##times_vd##SUF, av * bv, bv)                                              \
-    AD4CL_OP_DV(GS_T, PRE##times_dv##SUF, av * bv, TIMES_DV_DB)                                     \
-    AD4CL_OP_VV(GS_T, PRE##divide##SUF, av / bv, 1.0 / bv, -1.0 * val * (1.0 / bv))                 \
-    AD4CL_OP_VD(GS_T, PRE##divide_vd##SUF, av / bv, 1.0 / bv)                                       \
-    AD4CL_OP_DV(GS_T, PRE##divide_dv##SUF, av / bv, -1.0 * val * (1.0 / bv))
+    AD4CL_OP_VV(GS_T, PRE##minus##SUF, av - bv, 1.0, -1.0, 1, -1)                                      \
+    AD4CL_OP_VD(GS_T, PRE##minus_vd##SUF, av - bv, 1.0, 1)                                           \
+    AD4CL_OP_DV(GS_T, PRE##minus_dv##SUF, av - bv, -1.0, -1)                                         \
+    AD4CL_OP_VV(GS_T, PRE##times##SUF, av * bv, AD4CL_TIMES_DA, AD4CL_TIMES_DB, 0, 0)               \
+    AD4CL_OP_VD(GS_T, PRE##times_vd##SUF, av * bv, bv, 0)                                           \
+    AD4CL_OP_DV(GS_T, PRE##times_dv##SUF, av * bv, TIMES_DV_DB, 0)                                  \
+    AD4CL_OP_VV(GS_T, PRE##divide##SUF, av / bv, 1.0 / bv, -1.0 * val * (1.0 / bv), 0, 0)           \
+    AD4CL_OP_VD(GS_T, PRE##divide_vd##SUF, av / bv, 1.0 / bv, 0)                                    \
+    AD4CL_OP_DV(GS_T, PRE##divide_dv##SUF, av / bv, -1.0 * val * (1.0 / bv), 0)
 
 /* Math rows (ad.cl:926-1200 global, 1555-1829 private); partial expressions
  * are the reference's, e.g. pow(1 - pow(v,2), 0.5) rather than sqrt. */
@@ -291,9 +309,9 @@ AD4CL_DEV int record2(struct ad_private_gradient_structure* gs, double dx0, int 
     AD4CL_OP_V(GS_T, PRE##exp##SUF, exp(av), val)                                                   \
     AD4CL_OP_V(GS_T, PRE##log##SUF, log(av), 1.0 / av)                                              \
     AD4CL_OP_V(GS_T, PRE##log10##SUF, log10(av), 1.0 / (av * AD4CL_LN10))                           \
-    AD4CL_OP_VV(GS_T, PRE##pow##SUF, pow(av, bv), bv * pow(av, bv - (1.0)), log(av) * val)          \
-    AD4CL_OP_VD(GS_T, PRE##pow_vd##SUF, pow(av, bv), bv * pow(av, bv - (1.0)))                      \
-    AD4CL_OP_DV(GS_T, PRE##pow_dv##SUF, pow(av, bv), log(av) * val)                                 \
+    AD4CL_OP_VV(GS_T, PRE##pow##SUF, pow(av, bv), bv * pow(av, bv - (1.0)), log(av) * val, 0, 0)       \
+    AD4CL_OP_VD(GS_T, PRE##pow_vd##SUF, pow(av, bv), bv * pow(av, bv - (1.0)), 0)                   \
+    AD4CL_OP_DV(GS_T, PRE##pow_dv##SUF, pow(av, bv), log(av) * val, 0)                              \
     AD4CL_OP_V(GS_T, PRE##sqrt##SUF, sqrt(av), .5 / val)
 
 AD4CL_ARITHMETIC(struct ad_gradient_structure, ad_, , AD4CL_TIMES_DV_DB_QUIRKY)
@@ -313,9 +331,7 @@ AD4CL_DEV void pad_plus_eq_g(struct ad_gradient_structure* gs, struct ad_variabl
 
 /* Test / debug accessor: the `back`-th most recent slot of the thread tape (0 = last pushed). */
 AD4CL_DEV void ad4cl_tape_peek(const struct ad_gradient_structure* gs, int back, double* dx, int* word) {
-    const char* row = gs->tape->cur - (size_t) (back + 1) * ad4cl::kRowBytes;
-    *dx = *reinterpret_cast<const double*> (row);
-    *word = *reinterpret_cast<const int*> (row + gs->tape->id_off);
+    ad4cl::tape_read_row(gs->tape, gs->tape->next_id - gs->tape->first_temp - 1 - back, dx, word);
 }
 
 /*
@@ -325,8 +341,12 @@ AD4CL_DEV void ad4cl_tape_peek(const struct ad_gradient_structure* gs, int back,
  */
 AD4CL_DEV void ad_gradient_p(const struct ad_private_gradient_structure* gs, const struct ad_variable out,
         double* gradient) {
-    int p = gs->counter;
-    int s = gs->nslots < 2 * PRIVATE_STACK_SIZE ? gs->nslots : 2 * PRIVATE_STACK_SIZE;
+    int p = gs->counter; /* operators recorded */
+    int s = gs->nslots;
+    if (gs->overflow) { /* the stack stopped at the limit: count the operators it holds */
+        p = 0;
+        for (int i = 0; i < s; i++) p += (gs->slot_id[i] & ad4cl::kEndFlag) ? 1 : 0;
+    }
     gradient[out.id] = 1.0;
     double w = 0.0;
     while (s > 0) {
@@ -350,23 +370,30 @@ AD4CL_DEV void ad_gradient_p(const struct ad_private_gradient_structure* gs, con
  * are the independents (ids below gs->current_ad_variable_id).  The private stack lives in
  * registers / local memory, so only P slots per work-item reach the arena instead of one
  * slot per operand.  Ids on the private stack must be independents' ids or the private
- * stack's own results, i.e. pgs->current_ad_variable_id >= gs->current_ad_variable_id, and
- * every id must be below PRIVATE_GRADIENT_SIZE.
+ * stack's own results, i.e. pgs->current_ad_variable_id >= gs->current_ad_variable_id.
+ * A private stack that overflowed (more than PRIVATE_STACK_SIZE operators) or whose ids do
+ * not fit the private gradient (independents + operators > PRIVATE_GRADIENT_SIZE) is reported
+ * as a tape overflow (sticky status, the evaluation fails with AD4CL_ERR_TAPE_OVERFLOW)
+ * instead of being swept out of bounds.
  */
 AD4CL_DEV struct ad_variable ad_commit_p(struct ad_gradient_structure* gs,
         const struct ad_private_gradient_structure* pgs, const struct ad_variable out) {
     struct ad_variable ret = {out.value, 0};
     if (gs->recording != 1) return ret;
+    const int used = pgs->current_ad_variable_id + pgs->counter; /* ids the private stack can refer to */
+    if (pgs->overflow || used > PRIVATE_GRADIENT_SIZE || out.id < 0 || out.id >= used) {
+        gs->tape->status |= ad4cl::kErrTapeOverflow;
+        ad_init_var_g(gs, &ret, out.value);
+        return ret;
+    }
     double g[PRIVATE_GRADIENT_SIZE];
-    int used = pgs->current_ad_variable_id + pgs->counter; /* ids the private stack can refer to */
-    if (used > PRIVATE_GRADIENT_SIZE) used = PRIVATE_GRADIENT_SIZE;
     for (int i = 0; i < used; i++) g[i] = 0.0;
     ad_gradient_p(pgs, out, g);
     const int nparams = gs->current_ad_variable_id;
     int have = 0;
     for (int p = 0; p < nparams && p < PRIVATE_GRADIENT_SIZE; p++) {
         if (g[p] == 0.0) continue;
-        ret.id = have ? ad4cl::record2(gs, 1.0, ret.id, g[p], p) : ad4cl::record1(gs, g[p], p);
+        ret.id = have ? ad4cl::record2<1, 0>(gs, 1.0, ret.id, g[p], p) : ad4cl::record1<0>(gs, g[p], p);
         have = 1;
     }
     if (!have) ad_init_var_g(gs, &ret, out.value); /* constant: a leaf with no partials */

@@ -1,7 +1,17 @@
-/* ad4cl_builtin.h -- row type of the ahead-of-time kernel tables (builtin_kernels.cu). */
 #pragma once
+/* one row per ahead-of-time compiled kernel: name, its entry per accumulator mode (_m0/_m1/_m2), signature */
 struct ad4cl_builtin_row {
-    const char* name;        /* user kernel name */
-    const void* entry[3];    /* host handles of NAME__entry_m0/_m1/_m2 (accumulator mode) for cudaLaunchKernel */
-    const char* signature;   /* user kernel parameter kinds, see builtin_kernels.cu */
+    const char* name;
+    const void* entry[3];
+    const char* signature;
+};
+/* one row per register-tier instance (builtin_static.cu): valid for exactly `nparams` independents bound as
+   params(0, nparams) in signature order and, when frozen_arg >= 0, for that integer argument == frozen_value */
+struct ad4cl_static_row {
+    const char* name;
+    const void* entry;
+    const char* signature;
+    int nparams;
+    int frozen_arg;
+    int frozen_value;
 };

@@ -26,17 +26,28 @@
 
 namespace ad4cl {
 
+constexpr int kMaxWorld = 16;          /* ranks of a one-shot all-reduce group (one box) */
+constexpr int kInKernelPackMax = 4096; /* independents a CTA converts to ad_variables itself */
+
+/* One-shot all-reduce group as seen by this rank (filled from an ad4cl_comm; world <= 1: none). */
+struct CommInfo {
+    double* inbox[kMaxWorld];       /* rank r's inbox [2 parities][world][stride] as mapped into this process */
+    unsigned long long* epoch;      /* this rank's evaluation counter (device memory: graph replays advance it) */
+    int rank, world, stride;        /* stride = doubles per slot, the last one is the arrival flag */
+    unsigned long long timeout_ns;  /* a peer that has not arrived after this long fails the evaluation */
+};
+
 struct LaunchInfo {
-    long long n_items;      /* global work size (product over dimensions) */
-    int g0;                 /* global size of dimension 0 (dimension 1 = n_items / g0) */
+    long long n_items;      /* global work size (product over dimensions, padded to whole work-groups) */
+    int g0;                 /* global size of dimension 0, padded (dimension 1 = n_items / g0) */
+    int g0_user;            /* global size of dimension 0 as configured: out[] is indexed with it */
     int l0;                 /* local size of dimension 0 (local size 1 = blockDim.x / l0) */
     int nparams;            /* independents: ids 0..nparams-1 */
     int recording;          /* 1: objective + gradient, 0: objective only */
     int acc_mode;           /* AccMode */
-    int window;             /* adjoint ring entries per thread (power of two) */
+    int window;             /* adjoint ring entries per thread (power of two >= 4) */
     int use_far;            /* far-adjoint plane present in the arena */
-    int tape_in_smem;       /* 1: tape rows live in dynamic shared memory */
-    int sweep_prefetch;     /* 1: the sweep prefetches two batches ahead into L2 (ad4cl_tape.cuh) */
+    int tape_in_smem;       /* 1: tape planes live in dynamic shared memory */
     unsigned cap_slots;     /* per-thread tape capacity (operand slots) */
     char* arena;            /* HBM arena: one warp region per resident warp */
     unsigned long long warp_region;  /* bytes per warp region */
@@ -46,6 +57,15 @@ struct LaunchInfo {
     double* retain_meta;    /* non-null: RECORD ONLY.  One work-group per CTA (grid = number of groups), no
                                sweep, every thread keeps its tape in its own arena column and writes
                                {out.value, out.id, slots} here, 3 doubles per work-item (tape export path) */
+    /* ---- single-launch evaluation (round 2): parameter packing and the second reduction stage in this kernel */
+    const double* theta;    /* non-null: nparams plain doubles; every CTA converts them into `params` first */
+    struct ad_variable* params; /* the {value, id = i} array the user kernel's V arguments point into */
+    unsigned* ticket;       /* non-null: the CTA that finishes last reduces `partials` in fixed order into `result` */
+    double* result;         /* [grad (nparams), f or S, ops, slots] */
+    double* status_out;     /* non-null: receives (double) *status next to the result (one D2H copy for both) */
+    int epilogue;           /* 1: f = (n/2) log S, grad *= (n/2) / S  (simple.cpp:365) */
+    double n_obs;
+    CommInfo comm;          /* world > 1: the last CTA also all-reduces the raw sums with the peers */
 };
 
 /* Per-thread NDRange coordinates, published for get_global_id() and friends. */
@@ -84,7 +104,7 @@ extern __shared__ __align__(16) unsigned char ad4cl_dyn_smem[];
  *                                   after the last work-item (the region is max((window+1)*B, NW*ncols) doubles)
  *   thread_acc[nparams][B]          kAccThread only
  *   warp_acc  [NW][nparams]         kAccWarp only
- *   tape rows [NW][smem_region]     tape_in_smem only (bytes)
+ *   tape      [NW][warp region]     tape_in_smem only (bytes)
  */
 __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int window, int acc_mode,
         bool tape_in_smem, unsigned cap_slots, bool far) {
@@ -100,6 +120,211 @@ __host__ __device__ inline size_t entry_smem_bytes(int block, int nparams, int w
     return bytes;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+/*
+ * One-shot all-reduce of the short raw-sum vector over NVLink peer memory, by ONE CTA (the last one
+ * of the evaluation kernel, or the stand-alone kernel of ad4cl_cuda_comm_allreduce).  Every rank
+ * stores its vector into slot [parity][rank] of EVERY rank's inbox (peer stores), publishes a flag
+ * carrying the epoch, waits until all `world` flags of its own inbox show the epoch and sums the
+ * slots in rank order -- all ranks obtain bit-identical results, the order does not depend on who
+ * arrives first, and the latency is one NVLink store + one flag flight.  Two parities: a rank can
+ * run at most one epoch ahead of the slowest.  `v` (shared or global memory, n doubles) holds this
+ * rank's vector on entry and the sum over ranks on return; returns false after a timeout, with
+ * NaN in v (a communicator that timed out must be rebuilt: its epochs are no longer aligned).
+ */
+__device__ __forceinline__ bool oneshot_allreduce_cta(const CommInfo& C, double* v, int n, unsigned long long epoch) {
+    const int tid = threadIdx.x, B = blockDim.x;
+    const size_t slot_of_me = ((size_t) (epoch & 1) * C.world + C.rank) * C.stride;
+    for (int idx = tid; idx < C.world * n; idx += B) {
+        const int r = idx / n, i = idx - r * n;
+        C.inbox[r][slot_of_me + i] = v[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < C.world) {
+        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*> (C.inbox[tid] + slot_of_me + C.stride - 1);
+        *flag = epoch;
+    }
+    double* mine = C.inbox[C.rank] + (size_t) (epoch & 1) * C.world * C.stride;
+    __shared__ int failed;
+    if (tid == 0) failed = 0;
+    __syncthreads();
+    if (tid < C.world) {
+        const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*> (mine + (size_t) tid * C.stride + C.stride - 1);
+        const unsigned long long t0 = global_timer_ns();
+        while (*flag != epoch) {
+            if (global_timer_ns() - t0 > C.timeout_ns) { /* a peer never arrived: report instead of hanging */
+                failed = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const bool ok = failed == 0;
+    for (int i = tid; i < n; i += B) {
+        double s = 0.0;
+        for (int r = 0; r < C.world; r++) s += *reinterpret_cast<const volatile double*> (mine + (size_t) r * C.stride + i);
+        v[i] = ok ? s : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    __syncthreads();
+    return ok;
+}
+
+/* the reference's scalar epilogue on the reduced vector [grad (P), S, ...]  (simple.cpp:365, main.cpp:417) */
+__device__ __forceinline__ double apply_epilogue(double v, int c, int nparams, double S, double n_obs) {
+    if (c < nparams) return v * ((n_obs / 2.0) * (1.0 / S));
+    if (c == nparams) return (n_obs / 2.0) * log(S);
+    return v;
+}
+
+/*
+ * Second reduction stage, run by the CTA that finishes LAST (ticket): sums the per-block partial
+ * rows in a fixed order (column c by warp c mod NW; lane l adds blocks l, l+32, ... ascending, then
+ * the xor butterfly), so the result is bit-reproducible for a given launch shape regardless of
+ * which CTA happens to be last.  Then the all-reduce over ranks (if any), the epilogue, the result.
+ * `scratch` holds ncols doubles of shared memory.
+ */
+__device__ __forceinline__ void finish_evaluation(const LaunchInfo& L, int ncols, int ngrad, double* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int nblocks = gridDim.x;
+    for (int c = warp; c < ncols; c += nw) {
+        double v = 0.0;
+        for (int b = lane; b < nblocks; b += 32) v += __ldcg(L.partials + (size_t) b * ncols + c);
+        v = warp_sum(v);
+        if (lane == 0) scratch[c] = v;
+    }
+    __syncthreads();
+    bool ok = true;
+    if (L.comm.world > 1) {
+        __shared__ unsigned long long epoch_s;
+        if (tid == 0) epoch_s = ++(*L.comm.epoch);
+        __syncthreads();
+        ok = oneshot_allreduce_cta(L.comm, scratch, ncols, epoch_s);
+        if (!ok && tid == 0) atomicOr(L.status, 4);
+    }
+    const double S = scratch[ngrad];
+    for (int c = tid; c < ncols; c += blockDim.x) {
+        double v = scratch[c];
+        if (L.epilogue == 1 && ngrad == L.nparams) v = apply_epilogue(v, c, ngrad, S, L.n_obs);
+        L.result[(ngrad == L.nparams ? 0 : L.nparams) + c] = v;
+    }
+    if (tid == 0) {
+        if (L.status_out != nullptr) *L.status_out = (double) *reinterpret_cast<volatile int*> (L.status);
+        *L.ticket = 0u; /* ready for the next evaluation */
+    }
+}
+
+#if AD4CL_TAPE_STATIC
+/*
+ * The evaluation kernel of the REGISTER tier (ad4cl_tape.cuh): same persistent walk over the
+ * work-groups, but the tape, the adjoints and the gradient accumulators of a thread are registers.
+ * The user kernel receives LOCAL copies of the independents, th[p] = {theta_p, id = p} with literal
+ * ids, so that every index of the unrolled forward and reverse code is a compile-time constant.
+ * No warp-level operation inside the work-item loop: divergent kernels need no special care here.
+ * Dynamic shared memory: NW * (AD4CL_P + 3) doubles (block reduction scratch).
+ */
+template <int RECORDING, typename Body>
+__device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&& body) {
+    constexpr int P = AD4CL_P;
+    constexpr int ncols = P + 3;
+    const int B = blockDim.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nw = B >> 5;
+    double* red = reinterpret_cast<double*> (ad4cl_dyn_smem);
+    if (tid == 0) ad4cl_local_size0 = L.l0;
+    __syncthreads();
+
+    struct ad_variable th[P > 0 ? P : 1];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        th[p].value = L.theta[p];
+        th[p].id = p;
+    }
+    double g[P > 0 ? P : 1];
+#pragma unroll
+    for (int p = 0; p < P; p++) g[p] = 0.0;
+
+    double sum = 0.0;
+    long long total_ops = 0, total_slots = 0;
+    int status = kOk;
+    const long long ngroups = (L.n_items + B - 1) / B;
+    const int groups0 = L.g0 / L.l0;
+    const int l1 = B / L.l0;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        /* a FRESH tape per work-item: nothing loop-carried stands between the stores of the forward
+           pass and the loads of the sweep, so the compiler sees the id words as the constants they are */
+        ThreadTape tape;
+        tape_bind_static(tape);
+        const int grp0 = (int) (grp % groups0), grp1 = (int) (grp / groups0);
+        const int gid0 = grp0 * L.l0 + tid % L.l0;
+        const int gid1 = grp1 * l1 + tid / L.l0;
+        ad4cl_item_ids[tid].gid0 = gid0;
+        ad4cl_item_ids[tid].gid1 = gid1;
+        const long long out_index = (long long) gid1 * L.g0_user + gid0;
+
+        struct ad_gradient_structure gs;
+        gs.gradient_stack = nullptr;
+        gs.current_ad_variable_id = P;
+        gs.stack_current = 0;
+        gs.recording = RECORDING; /* a literal: every operator's `if (gs->recording == 1)` folds */
+        gs.counter = 0;
+        gs.index = nullptr;
+        gs.tape = &tape;
+
+        struct ad_variable outv = {0.0, kNoId};
+        body(&gs, &outv - out_index, th);
+        sum += outv.value;
+        if (RECORDING == 1 && tape.status == kOk) tape_sweep_static(tape, outv.id, g);
+        total_ops += tape.nops;
+        total_slots += tape.next_id - P;
+        status |= tape.status;
+    }
+
+    /* ---- block reduction: warp shuffles, then warps in fixed order ---- */
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const double v = warp_sum(g[p]);
+        if (lane == 0) red[(size_t) warp * ncols + p] = v;
+    }
+    {
+        const double s = warp_sum(sum);
+        const double o = warp_sum((double) total_ops);
+        const double k = warp_sum((double) total_slots);
+        if (lane == 0) {
+            red[(size_t) warp * ncols + P] = s;
+            red[(size_t) warp * ncols + P + 1] = o;
+            red[(size_t) warp * ncols + P + 2] = k;
+        }
+    }
+    const int st = __reduce_or_sync(0xffffffffu, status);
+    if (lane == 0 && st != 0) atomicOr(L.status, st);
+    __syncthreads();
+    double mine = 0.0;
+    if (tid < ncols) {
+        for (int wi = 0; wi < nw; wi++) mine += red[(size_t) wi * ncols + tid];
+        L.partials[(size_t) blockIdx.x * ncols + tid] = mine;
+    }
+    if (L.ticket != nullptr) {
+        __shared__ unsigned last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last = atomicAdd(L.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            finish_evaluation(L, ncols, P, red);
+        }
+    }
+}
+#else
 template <int MODE, typename Body>
 __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) {
     const int B = blockDim.x;
@@ -127,12 +352,20 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     if (MODE == kAccWarp)
         for (int i = tid; i < nw * P; i += B) warp_acc[i] = 0.0;
     if (tid == 0) ad4cl_local_size0 = L.l0;
+    /* ad_init_var (ad4cl.h:90-93) for the independents: {theta_i, id = i}.  Every CTA writes the same
+       values, and reads them only after its own barrier below. */
+    if (L.theta != nullptr) {
+        for (int i = tid; i < P; i += B) {
+            L.params[i].value = L.theta[i];
+            L.params[i].id = i;
+        }
+    }
 
     char* region;
     if (L.tape_in_smem) {
         region = reinterpret_cast<char*> (ad4cl_dyn_smem) + dbl_bytes + (size_t) warp * L.warp_region;
         if (L.use_far) { /* the far plane must start clear */
-            double* fa = reinterpret_cast<double*> (region + (size_t) (L.cap_slots + kGuardRows) * kRowBytes);
+            double* fa = reinterpret_cast<double*> (region + region_layout(L.cap_slots, true).off_far);
             for (int i = lane; i < (int) (L.cap_slots + kGuardRows) * 32; i += 32) fa[i] = 0.0;
         }
     } else {
@@ -162,6 +395,10 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         ad4cl_item_ids[tid].gid0 = gid0;
         ad4cl_item_ids[tid].gid1 = gid1;
         const long long item = (long long) gid1 * L.g0 + gid0;
+        /* The user's `out` is virtual: out[gid0 + g0_user * gid1] is a register of this thread.  The
+           index convention is the reference's own (simple.cl:137 out[id], matrixmul.cl:27
+           C[i + widthA * j] with widthA = global size 0); a kernel must write its own element only. */
+        const long long out_index = (long long) gid1 * L.g0_user + gid0;
 
         struct ad_gradient_structure gs;
         gs.gradient_stack = nullptr;
@@ -173,7 +410,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         gs.tape = &tape;
 
         struct ad_variable outv = {0.0, kNoId};
-        body(&gs, &outv - item);
+        body(&gs, &outv - out_index);
         sum += outv.value;
         if (L.retain_meta != nullptr) { /* tape export: leave the rows in the arena for the host */
             double* m = L.retain_meta + 3 * item;
@@ -183,7 +420,18 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
             continue;
         }
         /* a thread whose tape overflowed skips the sweep (the host reports the error) */
-        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) tape_sweep<MODE>(tape, outv.id, T, L.sweep_prefetch != 0);
+        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
+            /* ONE vote: every lane recorded every row uniformly and all lanes seed the same id */
+            int same = 0;
+            __match_all_sync(0xffffffffu, tape_is_uniform(tape) ? outv.id : -2 - lane, &same);
+            if (same) {
+                tape_sweep_uniform<MODE>(tape, outv.id, T);
+            } else {
+                tape.status |= tape_sweep_general<MODE>(tape.hdr, tape.cells, tape.lane_words, tape.far_adj,
+                        tape.next_id - tape.first_temp, tape.first_temp, tape.wm1, outv.id, T,
+                        (int) L.cap_slots + kGuardRows);
+            }
+        }
         tape_rewind(tape);
     }
 
@@ -216,7 +464,22 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         for (int wi = 0; wi < nw; wi++) v += red[(size_t) wi * ncols + c];
         L.partials[(size_t) blockIdx.x * ncols + c] = v;
     }
+
+    /* ---- second stage in the same launch: the CTA that finishes last sums the rows of all CTAs ---- */
+    if (L.ticket != nullptr) {
+        __shared__ unsigned last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last = atomicAdd(L.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            finish_evaluation(L, ncols, PR, red);
+        }
+    }
 }
+
+#endif /* AD4CL_TAPE_STATIC */
 
 } // namespace ad4cl
 
@@ -239,6 +502,29 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 /* one __global__ function per accumulator mode, so a launch only brings the code of
    the sweep it uses into the instruction cache: NAME__entry<suffix>_m0 / _m1 / _m2 */
 #define AD4CL_ENTRY_NAME(NAME, MODE) AD4CL_CAT4(NAME, __entry, AD4CL_ENTRY_SUFFIX, _m##MODE)
+/*
+ * AD4CL_STATIC_ENTRY(NAME, (typed user parameters), (call arguments)): the register-tier entry
+ * `NAME__entry<suffix>_s` (needs -DAD4CL_TAPE_STATIC=1 -DAD4CL_P=<independents>).  Same parameter list as
+ * the dynamic entry, so the shim marshals both alike; inside the call-argument list `th` is the local array
+ * of the independents (pass `th + first_id` where the dynamic entry forwards an ad_variable pointer) and
+ * integer arguments that bound loops should be written as literals.
+ */
+#if AD4CL_TAPE_STATIC
+#define AD4CL_STATIC_ENTRY_NAME(NAME) AD4CL_CAT4(NAME, __entry, AD4CL_ENTRY_SUFFIX, _s)
+#define AD4CL_STATIC_ENTRY(NAME, PARAMS, ARGS)                                             \
+    extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK)                           \
+    AD4CL_STATIC_ENTRY_NAME(NAME)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
+        auto body = [&](struct ad_gradient_structure* gs, struct ad_variable* out,         \
+                struct ad_variable* th) {                                                  \
+            struct ad_entry* gradient_stack = nullptr;                                     \
+            (void) gradient_stack; (void) th;                                              \
+            NAME(AD4CL_UNPAREN ARGS);                                                      \
+        };                                                                                 \
+        if (L.recording == 1) ad4cl::run_objective_static<1>(L, body);                     \
+        else ad4cl::run_objective_static<0>(L, body);                                      \
+    }
+#endif
+#if !AD4CL_TAPE_STATIC
 #define AD4CL_OBJECTIVE_ENTRY_MODE(NAME, MODE, PARAMS, ARGS)                               \
     extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK, AD4CL_MIN_BLOCKS)        \
     AD4CL_ENTRY_NAME(NAME, MODE)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
@@ -252,3 +538,4 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 0, PARAMS, ARGS)                                      \
     AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 1, PARAMS, ARGS)                                      \
     AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 2, PARAMS, ARGS)
+#endif /* !AD4CL_TAPE_STATIC */

@@ -1,9 +1,10 @@
 /*
  * shim.cu -- implementation of the C ABI declared in include/ad4cl_cuda.h.
  *
- * Host-side orchestration only: resource sizing, argument marshalling, the
- * three launches of one evaluation (pack parameters, fused record+sweep+block
- * reduction, fixed-order second stage) and the two small PCIe copies.  The
+ * Host-side orchestration only: resource sizing, argument marshalling, the ONE
+ * launch of an evaluation (parameter packing, record + sweep, both reduction
+ * stages and -- multi-GPU -- the one-shot all-reduce all happen inside the
+ * user kernel's entry, ad4cl_entry.cuh) and the two small PCIe copies.  The
  * arithmetic lives in ad.cuh / ad4cl_tape.cuh / ad4cl_entry.cuh.
  *
  * No CPU path exists here: every entry point needs a CUDA device.
@@ -183,21 +184,25 @@ struct ad4cl_kernel {
     int nparams = -1;
     int block = 0, grid = 0;
     size_t smem = 0, arena_bytes = 0;
+    int launches_per_eval = 1;
     ad4cl::LaunchInfo L{};
     long long data_items = 0;
     struct ad_variable* params_dev = nullptr;
+    double* theta_dev = nullptr;                 /* staging for the host path: nparams plain doubles */
+    unsigned* ticket_dev = nullptr;              /* last-CTA ticket of the fused second stage */
+    bool fused = false;                          /* one launch per evaluation (acc != global, nparams <= kInKernelPackMax) */
     double* partials = nullptr;
     double* result_dev = nullptr;
     double* global_grad = nullptr;
     int* status_dev = nullptr;
     char* arena = nullptr;
-    struct ad_variable* params_pinned = nullptr; /* host-packed {theta_i, id = i}: no pack kernel on the host path */
+    double* theta_pinned = nullptr;              /* the caller's theta, staged for the asynchronous H2D copy */
     double* result_pinned = nullptr;             /* nparams + 4 doubles: [grad, f, ops, slots, status] */
     int* status_pinned = nullptr;
     /* the host evaluation path replayed as one CUDA graph: [0] objective only, [1] with gradient */
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    ad4cl_comm* graph_comm = nullptr;   /* the communicator the captured graphs were built with */
     bool graph_disabled = false;
-    bool tune_pending = false;   /* AD4CL_PREFETCH_AUTO: decided by autotune_prefetch on the first gradient evaluation */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ad4cl_eval_stats stats{};
     /* opt-in timing of the fused kernel alone (ad4cl_cuda_kernel_profile) */
@@ -217,9 +222,10 @@ struct ad4cl_kernel {
     void release() {
         cudaFree(params_dev); cudaFree(partials); cudaFree(result_dev);
         cudaFree(global_grad); cudaFree(status_dev); cudaFree(arena);
+        cudaFree(theta_dev); cudaFree(ticket_dev);
         cudaFreeHost(result_pinned); cudaFreeHost(status_pinned);
-        cudaFreeHost(params_pinned);
-        params_pinned = nullptr;
+        cudaFreeHost(theta_pinned);
+        theta_pinned = nullptr; theta_dev = nullptr; ticket_dev = nullptr;
         drop_graphs();
         params_dev = nullptr; partials = nullptr; result_dev = nullptr;
         global_grad = nullptr; status_dev = nullptr; arena = nullptr;
@@ -303,9 +309,12 @@ int prepare(ad4cl_kernel* k, int nparams) {
     const int max_ops = std::max(c.max_ops, 1);
     const unsigned cap_slots = (unsigned) (c.max_slots > 0 ? c.max_slots : 2 * max_ops);
     const bool far = c.far_plane != 0;
-    int window = c.window > 0 ? pow2_at_least(c.window) : (far ? 16 : pow2_at_least(max_ops + 1));
+    /* without the far plane the ring must reach every operand: the distance is counted in SLOTS */
+    int window = c.window > 0 ? pow2_at_least(c.window) : (far ? 16 : pow2_at_least((int) cap_slots + 1));
+    window = std::max(window, 4); /* the uniform sweep pops a batch of 4 consecutive ring entries */
     int tier = c.tape_tier;
     if (tier == AD4CL_TAPE_AUTO) tier = AD4CL_TAPE_HBM;
+    const bool fused = acc != AD4CL_ACC_GLOBAL && nparams <= ad4cl::kInKernelPackMax;
 
     const size_t smem = ad4cl::entry_smem_bytes(block, nparams, window, acc, tier == AD4CL_TAPE_SHARED,
             cap_slots, far);
@@ -343,8 +352,10 @@ int prepare(ad4cl_kernel* k, int nparams) {
         CUDA_TRY(cudaMemset(k->arena, 0, arena_bytes)); /* far bitmaps must start clear */
     }
     CUDA_TRY(cudaMallocHost(&k->result_pinned, sizeof (double) * (size_t) (ncols + 1)));
-    CUDA_TRY(cudaMallocHost(&k->params_pinned, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
-    memset(k->params_pinned, 0, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1));
+    CUDA_TRY(cudaMallocHost(&k->theta_pinned, sizeof (double) * (size_t) std::max(nparams, 1)));
+    CUDA_TRY(cudaMalloc(&k->theta_dev, sizeof (double) * (size_t) std::max(nparams, 1)));
+    CUDA_TRY(cudaMalloc(&k->ticket_dev, sizeof (unsigned)));
+    CUDA_TRY(cudaMemset(k->ticket_dev, 0, sizeof (unsigned)));
     CUDA_TRY(cudaMallocHost(&k->status_pinned, sizeof (int)));
     if (!k->ev0) CUDA_TRY(cudaEventCreate(&k->ev0));
     if (!k->ev1) CUDA_TRY(cudaEventCreate(&k->ev1));
@@ -352,6 +363,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     ad4cl::LaunchInfo& L = k->L;
     L.n_items = g0 * g1;
     L.g0 = (int) g0;
+    L.g0_user = (int) c.global_size[0];
     L.l0 = l0;
     L.nparams = nparams;
     L.recording = 1;
@@ -359,15 +371,16 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.window = window;
     L.use_far = far ? 1 : 0;
     L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
-    L.sweep_prefetch = c.sweep_prefetch == AD4CL_PREFETCH_ON ? 1 : 0;
-    k->tune_pending = c.sweep_prefetch == AD4CL_PREFETCH_AUTO && tier != AD4CL_TAPE_SHARED; /* a no-op on a shared-memory tape */
-    k->stats.sweep_prefetch = k->tune_pending ? -1 : L.sweep_prefetch;
+    k->stats.sweep_prefetch = 0; /* round 2: the compact tape stays L2 resident where the prefetch used to pay; the option is accepted and ignored */
     L.cap_slots = cap_slots;
     L.arena = k->arena;
     L.warp_region = region;
     L.partials = k->partials;
     L.global_grad = k->global_grad;
     L.status = k->status_dev;
+    L.params = k->params_dev;
+    L.comm.world = 1;
+    k->fused = fused;
 
     k->block = block;
     k->grid = grid;
@@ -399,18 +412,58 @@ int drain_profile(ad4cl_kernel* k) {
     return AD4CL_OK;
 }
 
-/* enqueue pack + fused kernel + second stage on the context's stream */
+/*
+ * Enqueue one evaluation on the context's stream.  theta_dev: nparams plain doubles in device memory.
+ * Normal case (k->fused): ONE launch -- the entry converts theta to ad_variables, records, sweeps,
+ * reduces per block, and the CTA that finishes last runs the second stage, the all-reduce over the
+ * ranks of `comm` (if any) and the epilogue.  With fp64-atomic accumulation (matrix configs: 2 n^2
+ * independents) the parameters are packed and the partial rows reduced by separate small launches.
+ */
 int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue,
-        double* status_out = nullptr) {
+        double* status_out = nullptr, ad4cl_comm* comm = nullptr);
+
+int status_to_error(ad4cl_kernel* k, int st);
+
+} // namespace
+
+struct ad4cl_comm {
+    ad4cl_context* ctx = nullptr;
+    int rank = 0, world = 1, stride = 0;
+    double* inbox = nullptr;           /* [2][world][stride] */
+    ad4cl::CommInfo info{};            /* peers' inboxes as mapped into this process, epoch counter, timeout */
+    bool connected = false;
+    bool local_group = false;          /* created by ad4cl_cuda_comm_create_local: peers are plain pointers, not IPC mappings */
+    int* status_dev = nullptr;
+    int* status_pinned = nullptr;
+};
+
+namespace {
+
+int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue,
+        double* status_out, ad4cl_comm* comm) {
     cudaStream_t st = k->ctx->stream;
     const int P = k->nparams;
-    if (P > 0 && theta_dev != nullptr) { /* nullptr: params_dev was filled by the caller (host path) */
-        pack_params<<<(P + 127) / 128, 128, 0, st>>>(theta_dev, k->params_dev, P);
-    }
+    if (comm != nullptr && comm->world > 1 && !k->fused)
+        return fail(AD4CL_ERR_INVALID, "kernel %s: the sharded evaluation needs the fused second stage "
+                "(accumulator mode thread or warp, at most %d independents)", k->name.c_str(), ad4cl::kInKernelPackMax);
     ad4cl::LaunchInfo L = k->L;
     L.recording = want_gradient ? 1 : 0;
-    if (k->global_grad)
-        CUDA_TRY(cudaMemsetAsync(k->global_grad, 0, sizeof (double) * (size_t) std::max(P, 1), st));
+    const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
+    const int epi = apply_epilogue ? k->cfg.epilogue : 0;
+    if (k->fused) {
+        L.theta = P > 0 ? theta_dev : nullptr;
+        L.ticket = k->ticket_dev;
+        L.result = result_dev;
+        L.status_out = status_out;
+        L.epilogue = epi;
+        L.n_obs = n_obs;
+        if (comm != nullptr && comm->world > 1) L.comm = comm->info;
+    } else {
+        if (P > 0 && theta_dev != nullptr)
+            pack_params<<<(P + 255) / 256, 256, 0, st>>>(theta_dev, k->params_dev, P);
+        if (k->global_grad)
+            CUDA_TRY(cudaMemsetAsync(k->global_grad, 0, sizeof (double) * (size_t) std::max(P, 1), st));
+    }
 
     /* marshal: LaunchInfo first, then the user kernel's non-runtime parameters in order */
     std::vector<void*> argv;
@@ -464,58 +517,22 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
         if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuLaunchKernel(%s) failed: %d", k->name.c_str(), (int) r);
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
-    const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
-    const int epi = apply_epilogue ? k->cfg.epilogue : 0;
-    if (k->global_grad) {
-        ad4cl_reduce_partials<<<3, 256, 0, st>>>(k->partials, k->grid, 3, 0, P, epi, n_obs, result_dev,
-                k->status_dev, status_out);
-        if (P > 0)
-            ad4cl_finish_global_grad<<<(P + 255) / 256, 256, 0, st>>>(k->global_grad, P, k->partials, k->grid,
-                    epi, n_obs, result_dev);
-    } else {
-        ad4cl_reduce_partials<<<P + 3, 256, 0, st>>>(k->partials, k->grid, P + 3, P, 0, epi, n_obs, result_dev,
-                k->status_dev, status_out);
-    }
-    CUDA_TRY(cudaGetLastError());
-    return AD4CL_OK;
-}
-
-/*
- * AD4CL_PREFETCH_AUTO: time the evaluation (pack + fused kernel + second stage, CUDA events on the
- * context's stream) with the sweep's L2 prefetch off and on, and keep the faster setting for this
- * configuration.  Runs once, on the first gradient evaluation, before the CUDA graph is captured.
- * An evaluation longer than 50 ms is tape streaming at HBM speed, where the prefetch was never
- * measured to help: it stays off without a second run.  The choice cannot change a result bit.
- */
-int autotune_prefetch(ad4cl_kernel* k, const double* theta_dev) {
-    cudaStream_t st = k->ctx->stream;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
-        cudaGetLastError();
-        return AD4CL_OK; /* a caller-owned stream under graph capture cannot be timed: stay off, decide on a later call */
-    }
-    k->tune_pending = false;
-    float best[2] = {1e30f, 1e30f};
-    for (int round = 0; round < 2; round++) {
-        for (int pf = 0; pf < 2; pf++) {
-            k->L.sweep_prefetch = pf;
-            CUDA_TRY(cudaEventRecord(k->ev0, st));
-            int rc = enqueue(k, theta_dev, k->result_dev, 1, 0);
-            if (rc != AD4CL_OK) return rc;
-            CUDA_TRY(cudaEventRecord(k->ev1, st));
-            CUDA_TRY(cudaEventSynchronize(k->ev1));
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, k->ev0, k->ev1));
-            if (round > 0 || pf > 0 || ms > 50.f) best[pf] = std::min(best[pf], ms); /* the very first run also warms up */
-            if (pf == 0 && ms > 50.f) {
-                round = 2;
-                break;
-            }
+    k->launches_per_eval = 1;
+    if (!k->fused) {
+        if (k->global_grad) {
+            ad4cl_reduce_partials<<<3, 256, 0, st>>>(k->partials, k->grid, 3, 0, P, epi, n_obs, result_dev,
+                    k->status_dev, status_out);
+            if (P > 0)
+                ad4cl_finish_global_grad<<<(P + 255) / 256, 256, 0, st>>>(k->global_grad, P, k->partials, k->grid,
+                        epi, n_obs, result_dev);
+            k->launches_per_eval = 2 + (P > 0 ? 2 : 0);
+        } else {
+            ad4cl_reduce_partials<<<P + 3, 256, 0, st>>>(k->partials, k->grid, P + 3, P, 0, epi, n_obs, result_dev,
+                    k->status_dev, status_out);
+            k->launches_per_eval = 2 + (P > 0 ? 1 : 0);
         }
     }
-    k->L.sweep_prefetch = best[1] < best[0] ? 1 : 0;
-    k->stats.sweep_prefetch = k->L.sweep_prefetch;
-    CUDA_TRY(cudaMemsetAsync(k->status_dev, 0, sizeof (int), st)); /* an error shows up again in the evaluation proper */
+    CUDA_TRY(cudaGetLastError());
     return AD4CL_OK;
 }
 
@@ -537,82 +554,27 @@ int status_to_error(ad4cl_kernel* k, int st) {
 } // namespace
 
 /*
- * One-shot all-reduce of a short fp64 vector over NVLink peer memory (one process per GPU).
- * Every rank stores its vector into slot [parity][rank] of EVERY rank's inbox (peer stores),
- * publishes a flag carrying the epoch, waits until all `world` flags of its own inbox show the
- * epoch, and sums the slots in rank order -- so all ranks obtain bit-identical results, the sum
- * order does not depend on arrival order, and the latency is one NVLink store + one flag flight
- * instead of a collective's ring/tree.  Two parities: a rank can run at most one epoch ahead.
- * The scalar epilogue of the objective is applied to the reduced vector in the same kernel.
+ * Stand-alone form of the one-shot all-reduce (ad4cl_cuda_comm_allreduce): the same CTA routine the
+ * evaluation kernel's last CTA runs (ad4cl_entry.cuh), in place on a device vector, epilogue fused.
  */
 namespace {
 
-struct CommPeers {
-    double* inbox[16]; /* rank r's inbox as mapped into this process (own inbox at [rank]) */
-};
-
-__global__ void __launch_bounds__(256) oneshot_allreduce(CommPeers peers, int rank, int world, int stride,
-        int n, unsigned long long epoch, double* __restrict__ data, int nparams, int epilogue, double n_obs,
-        int* __restrict__ status) {
-    const int tid = threadIdx.x;
-    const size_t slot_of_me = ((size_t) (epoch & 1) * world + rank) * stride;
-    for (int idx = tid; idx < world * n; idx += 256) {
-        const int r = idx / n, i = idx - r * n;
-        peers.inbox[r][slot_of_me + i] = data[i];
-    }
-    __threadfence_system();
+__global__ void __launch_bounds__(256) oneshot_allreduce_kernel(ad4cl::CommInfo C, int n, double* __restrict__ data,
+        int nparams, int epilogue, double n_obs, int* __restrict__ status) {
+    __shared__ unsigned long long epoch_s;
+    __shared__ double S_s;
+    if (threadIdx.x == 0) epoch_s = ++(*C.epoch);
     __syncthreads();
-    if (tid < world) {
-        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*> (peers.inbox[tid] + slot_of_me + stride - 1);
-        *flag = epoch;
-    }
-    double* mine = peers.inbox[rank] + (size_t) (epoch & 1) * world * stride;
-    __shared__ int failed;
-    if (tid == 0) failed = 0;
-    __syncthreads();
-    if (tid < world) {
-        const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*> (mine + (size_t) tid * stride + stride - 1);
-        const long long t0 = clock64();
-        while (*flag != epoch) {
-            if (clock64() - t0 > 4000000000LL) { /* ~2 s: a peer never arrived; report instead of hanging */
-                failed = 1;
-                break;
-            }
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (failed) {
-        if (tid == 0) atomicOr(status, 4);
-        return;
-    }
-    double S = 0.0;
-    if (epilogue == 1) {
-        for (int r = 0; r < world; r++) S += *reinterpret_cast<const volatile double*> (mine + (size_t) r * stride + nparams);
-    }
-    for (int i = tid; i < n; i += 256) {
-        double v = 0.0;
-        for (int r = 0; r < world; r++) v += *reinterpret_cast<const volatile double*> (mine + (size_t) r * stride + i);
-        if (epilogue == 1) {
-            if (i < nparams) v *= (n_obs / 2.0) * (1.0 / S);
-            else if (i == nparams) v = (n_obs / 2.0) * log(S);
-        }
-        data[i] = v;
+    const bool ok = ad4cl::oneshot_allreduce_cta(C, data, n, epoch_s);
+    if (!ok && threadIdx.x == 0) atomicOr(status, 4);
+    if (epilogue == 1 && ok) {
+        if (threadIdx.x == 0) S_s = data[nparams];
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) data[i] = ad4cl::apply_epilogue(data[i], i, nparams, S_s, n_obs);
     }
 }
 
 } // namespace
-
-struct ad4cl_comm {
-    ad4cl_context* ctx = nullptr;
-    int rank = 0, world = 1, stride = 0;
-    double* inbox = nullptr;           /* [2][world][stride] */
-    CommPeers peers{};
-    bool connected = false;
-    unsigned long long epoch = 0;
-    int* status_dev = nullptr;
-    int* status_pinned = nullptr;
-};
 
 /* ============================================================ C ABI */
 #pragma GCC visibility push(default)
@@ -962,11 +924,20 @@ int ad4cl_cuda_eval_device(ad4cl_kernel* k, const double* theta_dev, int nparams
     CUDA_TRY(cudaSetDevice(k->ctx->device));
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
-    if (k->tune_pending && want_gradient) {
-        rc = autotune_prefetch(k, theta_dev);
-        if (rc != AD4CL_OK) return rc;
-    }
     return enqueue(k, theta_dev, result_dev, want_gradient, apply_epilogue);
+}
+
+int ad4cl_cuda_eval_device_sharded(ad4cl_kernel* k, ad4cl_comm* comm, const double* theta_dev, int nparams,
+        double* result_dev, int want_gradient) {
+    if (!k || !comm || !result_dev || (!theta_dev && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    if (comm->ctx != k->ctx) return fail(AD4CL_ERR_INVALID, "communicator and kernel belong to different contexts");
+    if (!comm->connected && comm->world > 1) return fail(AD4CL_ERR_INVALID, "communicator is not connected");
+    if (nparams + 3 > comm->stride - 1)
+        return fail(AD4CL_ERR_INVALID, "vector of %d doubles exceeds the communicator's %d", nparams + 3, comm->stride - 1);
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    int rc = prepare(k, nparams);
+    if (rc != AD4CL_OK) return rc;
+    return enqueue(k, theta_dev, result_dev, want_gradient, 1, nullptr, comm);
 }
 
 int ad4cl_cuda_check(ad4cl_kernel* k) {
@@ -978,49 +949,47 @@ int ad4cl_cuda_check(ad4cl_kernel* k) {
     return status_to_error(k, *k->status_pinned);
 }
 
-/* the host path on the stream: parameters up, launches, [grad, f, ops, slots, status] down */
-static int enqueue_host_path(ad4cl_kernel* k, int want_gradient) {
+/* the host path on the stream: theta up, ONE launch, [grad, f, ops, slots, status] down */
+static int enqueue_host_path(ad4cl_kernel* k, int want_gradient, ad4cl_comm* comm) {
     cudaStream_t st = k->ctx->stream;
     const int P = k->nparams;
     if (P > 0)
-        CUDA_TRY(cudaMemcpyAsync(k->params_dev, k->params_pinned, sizeof (struct ad_variable) * (size_t) P,
-                cudaMemcpyHostToDevice, st));
-    int rc = enqueue(k, nullptr, k->result_dev, want_gradient, 1, k->result_dev + P + 3);
+        CUDA_TRY(cudaMemcpyAsync(k->theta_dev, k->theta_pinned, sizeof (double) * (size_t) P, cudaMemcpyHostToDevice, st));
+    int rc = enqueue(k, k->theta_dev, k->result_dev, want_gradient, 1, k->result_dev + P + 3, comm);
     if (rc != AD4CL_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(k->result_pinned, k->result_dev, sizeof (double) * (size_t) (P + 4), cudaMemcpyDeviceToHost, st));
     return AD4CL_OK;
 }
 
-int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f, double* grad) {
+static int eval_host(ad4cl_kernel* k, ad4cl_comm* comm, const double* theta, int nparams, double* f, double* grad) {
     if (!k || !f || (!theta && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(k->ctx->device));
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
     cudaStream_t st = k->ctx->stream;
     const int want = grad != nullptr ? 1 : 0;
-    for (int p = 0; p < nparams; p++) { /* ad_init_var, ad4cl.h:90-93: {value, id = p} */
-        k->params_pinned[p].value = theta[p];
-        k->params_pinned[p].id = p;
+    if (nparams > 0) memcpy(k->theta_pinned, theta, sizeof (double) * (size_t) nparams);
+    /* Replay the whole evaluation as one CUDA graph (captured on first use; the launch's
+       arguments are fixed until an argument, the configuration or the communicator changes; the
+       all-reduce epoch lives in device memory).  Profiling needs events around the kernel, so it
+       takes the plain path. */
+    if (k->graph_comm != comm) {
+        k->drop_graphs();
+        k->graph_comm = comm;
     }
-    if (k->tune_pending && want) {
-        if (nparams > 0)
-            CUDA_TRY(cudaMemcpyAsync(k->params_dev, k->params_pinned, sizeof (struct ad_variable) * (size_t) nparams,
-                    cudaMemcpyHostToDevice, st));
-        rc = autotune_prefetch(k, nullptr);
-        if (rc != AD4CL_OK) return rc;
-    }
-    /* Replay the whole evaluation as one CUDA graph (captured on first use; the launches'
-       arguments are fixed until an argument or the configuration changes).  Profiling needs
-       events around the fused kernel, so it takes the plain path. */
     const bool use_graph = !k->profiling && !k->graph_disabled;
     if (use_graph && !k->graph[want]) {
         cudaGraph_t g = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            rc = enqueue_host_path(k, want);
+            rc = enqueue_host_path(k, want, comm);
             cudaError_t e = cudaStreamEndCapture(st, &g);
             if (rc == AD4CL_OK && e == cudaSuccess && g && cudaGraphInstantiate(&k->graph[want], g, 0) != cudaSuccess)
                 k->graph[want] = nullptr;
             if (g) cudaGraphDestroy(g);
+            if (rc != AD4CL_OK) {
+                cudaGetLastError();
+                return rc; /* an argument error, not a capture problem */
+            }
         }
         if (!k->graph[want]) { /* capture unavailable on this stream: fall back to plain launches for good */
             cudaGetLastError();
@@ -1032,13 +1001,20 @@ int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f
         k->stats.kernel_ms = 0.f;
     } else {
         CUDA_TRY(cudaEventRecord(k->ev0, st));
-        rc = enqueue_host_path(k, want);
+        rc = enqueue_host_path(k, want, comm);
         if (rc != AD4CL_OK) return rc;
         CUDA_TRY(cudaEventRecord(k->ev1, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!(use_graph && k->graph[want])) CUDA_TRY(cudaEventElapsedTime(&k->stats.kernel_ms, k->ev0, k->ev1));
-    rc = status_to_error(k, (int) k->result_pinned[nparams + 3]);
+    const int status = (int) k->result_pinned[nparams + 3];
+    if (status & 4) {
+        cudaMemsetAsync(k->status_dev, 0, sizeof (int), st);
+        cudaStreamSynchronize(st);
+        return fail(AD4CL_ERR_CUDA, "kernel %s: the all-reduce timed out waiting for a peer (rank %d of %d); "
+                "the communicator must be rebuilt", k->name.c_str(), comm ? comm->rank : 0, comm ? comm->world : 1);
+    }
+    rc = status_to_error(k, status);
     if (rc != AD4CL_OK) return rc;
     *f = k->result_pinned[nparams];
     if (grad) memcpy(grad, k->result_pinned, sizeof (double) * (size_t) nparams);
@@ -1046,6 +1022,21 @@ int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f
     k->stats.slots = k->result_pinned[nparams + 2];
     return AD4CL_OK;
 }
+
+int ad4cl_cuda_eval(ad4cl_kernel* k, const double* theta, int nparams, double* f, double* grad) {
+    return eval_host(k, nullptr, theta, nparams, f, grad);
+}
+
+int ad4cl_cuda_eval_sharded(ad4cl_kernel* k, ad4cl_comm* comm, const double* theta, int nparams, double* f, double* grad) {
+    if (!comm) return fail(AD4CL_ERR_INVALID, "communicator is NULL");
+    if (k && comm->ctx != k->ctx) return fail(AD4CL_ERR_INVALID, "communicator and kernel belong to different contexts");
+    if (!comm->connected && comm->world > 1) return fail(AD4CL_ERR_INVALID, "communicator is not connected");
+    if (nparams + 3 > comm->stride - 1)
+        return fail(AD4CL_ERR_INVALID, "vector of %d doubles exceeds the communicator's %d", nparams + 3, comm->stride - 1);
+    return eval_host(k, comm, theta, nparams, f, grad);
+}
+
+int ad4cl_cuda_launches_per_eval(ad4cl_kernel* k) { return k ? k->launches_per_eval : 0; }
 
 int ad4cl_cuda_kernel_profile(ad4cl_kernel* k, int enable) {
     if (!k) return fail(AD4CL_ERR_INVALID, "kernel is NULL");
@@ -1075,10 +1066,11 @@ int ad4cl_cuda_kernel_profile_read(ad4cl_kernel* k, double* mean_ms, long long* 
     return AD4CL_OK;
 }
 
-int ad4cl_cuda_comm_create(ad4cl_context* ctx, int rank, int world, int max_doubles, ad4cl_comm** out) {
+static int comm_alloc(ad4cl_context* ctx, int rank, int world, int max_doubles, ad4cl_comm** out) {
     if (!ctx || !out) return fail(AD4CL_ERR_INVALID, "NULL argument");
-    if (world < 1 || world > 16 || rank < 0 || rank >= world || max_doubles < 1)
-        return fail(AD4CL_ERR_INVALID, "bad communicator shape rank=%d world=%d n=%d (world <= 16)", rank, world, max_doubles);
+    if (world < 1 || world > ad4cl::kMaxWorld || rank < 0 || rank >= world || max_doubles < 1)
+        return fail(AD4CL_ERR_INVALID, "bad communicator shape rank=%d world=%d n=%d (world <= %d)", rank, world,
+                max_doubles, ad4cl::kMaxWorld);
     CUDA_TRY(cudaSetDevice(ctx->device));
     ad4cl_comm* c = new ad4cl_comm();
     c->ctx = ctx;
@@ -1086,14 +1078,58 @@ int ad4cl_cuda_comm_create(ad4cl_context* ctx, int rank, int world, int max_doub
     c->world = world;
     c->stride = max_doubles + 1; /* + the flag word */
     const size_t bytes = sizeof (double) * 2 * (size_t) world * c->stride;
-    CUDA_TRY(cudaMalloc(&c->inbox, bytes));
-    CUDA_TRY(cudaMemset(c->inbox, 0, bytes));
+    CUDA_TRY(cudaMalloc(&c->inbox, bytes + sizeof (unsigned long long)));
+    CUDA_TRY(cudaMemset(c->inbox, 0, bytes + sizeof (unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->status_dev, sizeof (int)));
     CUDA_TRY(cudaMemset(c->status_dev, 0, sizeof (int)));
     CUDA_TRY(cudaMallocHost(&c->status_pinned, sizeof (int)));
     CUDA_TRY(cudaDeviceSynchronize());
-    c->peers.inbox[rank] = c->inbox;
+    c->info.inbox[rank] = c->inbox;
+    c->info.epoch = reinterpret_cast<unsigned long long*> (c->inbox + 2 * (size_t) world * c->stride);
+    c->info.rank = rank;
+    c->info.world = world;
+    c->info.stride = c->stride;
+    c->info.timeout_ns = 30ull * 1000000000ull; /* ad4cl_cuda_comm_set_timeout */
     *out = c;
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_create(ad4cl_context* ctx, int rank, int world, int max_doubles, ad4cl_comm** out) {
+    return comm_alloc(ctx, rank, world, max_doubles, out);
+}
+
+/* all ranks in ONE process (one context per GPU): peers are reached through plain peer access */
+int ad4cl_cuda_comm_create_local(ad4cl_context** ctxs, int world, int max_doubles, ad4cl_comm** comms_out) {
+    if (!ctxs || !comms_out) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    for (int r = 0; r < world; r++) comms_out[r] = nullptr;
+    for (int r = 0; r < world; r++) {
+        int rc = comm_alloc(ctxs[r], r, world, max_doubles, &comms_out[r]);
+        if (rc != AD4CL_OK) return rc;
+        comms_out[r]->local_group = true;
+    }
+    for (int r = 0; r < world; r++) {
+        CUDA_TRY(cudaSetDevice(ctxs[r]->device));
+        for (int q = 0; q < world; q++) {
+            if (q == r) continue;
+            if (ctxs[q]->device != ctxs[r]->device) {
+                int can = 0;
+                CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device));
+                if (!can) return fail(AD4CL_ERR_CUDA, "device %d cannot access device %d", ctxs[r]->device, ctxs[q]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(AD4CL_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctxs[r]->device, ctxs[q]->device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            comms_out[r]->info.inbox[q] = comms_out[q]->inbox;
+        }
+        comms_out[r]->connected = true;
+    }
+    return AD4CL_OK;
+}
+
+int ad4cl_cuda_comm_set_timeout(ad4cl_comm* c, double seconds) {
+    if (!c || !(seconds > 0.0)) return fail(AD4CL_ERR_INVALID, "bad timeout");
+    c->info.timeout_ns = (unsigned long long) (seconds * 1e9);
     return AD4CL_OK;
 }
 
@@ -1117,7 +1153,7 @@ int ad4cl_cuda_comm_connect(ad4cl_comm* c, const void* handles) {
         memcpy(&h, (const char*) handles + (size_t) r * sizeof h, sizeof h);
         void* p = nullptr;
         CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        c->peers.inbox[r] = (double*) p;
+        c->info.inbox[r] = (double*) p;
     }
     c->connected = true;
     return AD4CL_OK;
@@ -1128,9 +1164,7 @@ int ad4cl_cuda_comm_allreduce(ad4cl_comm* c, double* data_dev, int n, int nparam
     if (!c->connected && c->world > 1) return fail(AD4CL_ERR_INVALID, "communicator is not connected");
     if (n < 1 || n > c->stride - 1) return fail(AD4CL_ERR_INVALID, "vector of %d doubles exceeds the communicator's %d", n, c->stride - 1);
     CUDA_TRY(cudaSetDevice(c->ctx->device));
-    c->epoch++;
-    oneshot_allreduce<<<1, 256, 0, c->ctx->stream>>>(c->peers, c->rank, c->world, c->stride, n, c->epoch, data_dev,
-            nparams, epilogue, n_obs, c->status_dev);
+    oneshot_allreduce_kernel<<<1, 256, 0, c->ctx->stream>>>(c->info, n, data_dev, nparams, epilogue, n_obs, c->status_dev);
     CUDA_TRY(cudaGetLastError());
     return AD4CL_OK;
 }
@@ -1140,7 +1174,9 @@ int ad4cl_cuda_comm_check(ad4cl_comm* c) {
     CUDA_TRY(cudaSetDevice(c->ctx->device));
     CUDA_TRY(cudaMemcpyAsync(c->status_pinned, c->status_dev, sizeof (int), cudaMemcpyDeviceToHost, c->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(c->ctx->stream));
-    if (*c->status_pinned) return fail(AD4CL_ERR_CUDA, "one-shot all-reduce timed out waiting for a peer (rank %d of %d)", c->rank, c->world);
+    if (*c->status_pinned)
+        return fail(AD4CL_ERR_CUDA, "one-shot all-reduce timed out waiting for a peer (rank %d of %d): the reduced vector "
+                "holds NaN and the communicator must be rebuilt", c->rank, c->world);
     return AD4CL_OK;
 }
 
@@ -1148,8 +1184,9 @@ int ad4cl_cuda_comm_destroy(ad4cl_comm* c) {
     if (!c) return AD4CL_OK;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
-    for (int r = 0; r < c->world; r++)
-        if (r != c->rank && c->peers.inbox[r]) cudaIpcCloseMemHandle(c->peers.inbox[r]);
+    if (!c->local_group)
+        for (int r = 0; r < c->world; r++)
+            if (r != c->rank && c->info.inbox[r]) cudaIpcCloseMemHandle(c->info.inbox[r]);
     cudaFree(c->inbox);
     cudaFree(c->status_dev);
     cudaFreeHost(c->status_pinned);
@@ -1165,7 +1202,7 @@ int ad4cl_cuda_comm_destroy(ad4cl_comm* c) {
  * Ids: independents keep theirs; the temporaries of work-item i become first_free_id + (operators of
  * the work-items before i) + operator index.  In-place operators appear with a fresh result id (same
  * sweep result); a leaf (ad_init_var_g) appears as an entry of size 0.  Small problems only: the arena
- * holds n_items * (max_slots + 2) * 12 bytes.
+ * holds one warp region (ad4cl_tape.cuh: header, cell, lane-word and far planes) per 32 work-items.
  */
 int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, int first_free_id,
         void* entries_out, long long capacity, long long* n_entries, void* out_vars, long long n_out) {
@@ -1202,13 +1239,11 @@ int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, in
     k->L.retain_meta = meta;
     k->L.tape_in_smem = 0;
     k->grid = (int) ngroups;
-    for (int p = 0; p < nparams; p++) {
-        k->params_pinned[p].value = theta[p];
-        k->params_pinned[p].id = p;
+    if (nparams > 0) {
+        memcpy(k->theta_pinned, theta, sizeof (double) * (size_t) nparams);
+        CUDA_TRY(cudaMemcpyAsync(k->theta_dev, k->theta_pinned, sizeof (double) * (size_t) nparams, cudaMemcpyHostToDevice, st));
     }
-    if (nparams > 0)
-        CUDA_TRY(cudaMemcpyAsync(k->params_dev, k->params_pinned, sizeof (struct ad_variable) * (size_t) nparams, cudaMemcpyHostToDevice, st));
-    rc = enqueue(k, nullptr, k->result_dev, 1, 0);
+    rc = enqueue(k, k->theta_dev, k->result_dev, 1, 0);
     k->L = saved;
     k->grid = saved_grid;
     k->partials = saved_partials;
@@ -1241,6 +1276,7 @@ int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, in
         const long long grp = (gid1 / l1) * (g0 / l0) + gid0 / l0;
         const int tid = (int) ((gid1 % l1) * l0 + gid0 % l0);
         const char* col = rows.data() + ((size_t) grp * nw + tid / 32) * region;
+        const ad4cl::RegionLayout lay = ad4cl::region_layout(k->L.cap_slots, k->L.use_far != 0);
         const int lane = tid % 32;
         const int nslots = (int) m[3 * item + 2];
         op_of_slot.assign((size_t) nslots, -1);
@@ -1249,11 +1285,15 @@ int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, in
         HostEntry cur{};
         int have = 0;
         for (int s = 0; s < nslots; s++) {
-            const char* row = col + (size_t) s * ad4cl::kRowBytes;
+            /* header {id word, cell offset | flags}; a non-uniform row keeps its id word per lane */
+            int hdr[2];
+            memcpy(hdr, col + (size_t) s * ad4cl::kHdrBytes, 8);
+            const unsigned aux = (unsigned) hdr[1];
+            int word = hdr[0];
+            if (aux & ad4cl::kAuxNonUniform)
+                memcpy(&word, col + lay.off_lane_words + (size_t) s * ad4cl::kLaneWordRowBytes + lane * 4, 4);
             double dx;
-            int word;
-            memcpy(&dx, row + lane * 8, 8);
-            memcpy(&word, row + ad4cl::kRowIdOffset + lane * 4, 4);
+            memcpy(&dx, col + lay.off_cells + (aux & ad4cl::kAuxOffsetMask) + lane * 8, 8);
             if (!(word & ad4cl::kNopFlag)) {
                 const int payload = word & ad4cl::kIdMask;
                 const int id = (word & ad4cl::kParamFlag) ? payload : base + op_of_slot[(size_t) payload];

@@ -45,9 +45,9 @@ class ShardedObjective:
     the epilogue on the device."""
 
     def __init__(self, local_eval: Callable[[torch.Tensor, torch.Tensor], None], nparams: int,
-                 epilogue: str, n_total: int, device: torch.device, group=None, comm=None):
+                 epilogue: str, n_total: int, device: torch.device, group=None, comm=None, kernel=None):
         self.local_eval, self.P, self.epilogue, self.n_total = local_eval, nparams, epilogue, n_total
-        self.device, self.group, self.comm = device, group, comm
+        self.device, self.group, self.comm, self.kernel = device, group, comm, kernel
         self.raw = torch.zeros(nparams + 3, dtype=torch.float64, device=device)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
@@ -61,14 +61,22 @@ class ShardedObjective:
     def eval_device(self, theta: torch.Tensor) -> torch.Tensor:
         """-> [grad..., f, ops, slots] on the device, epilogue applied, no host synchronisation."""
         if self.comm is not None and self.world > 1:
+            if self.kernel is not None:
+                # ONE launch: the evaluation kernel's last CTA exchanges the raw sums with the peers over
+                # NVLink and applies the epilogue (ad4cl_cuda_eval_device_sharded)
+                self.kernel.eval_device_sharded(self.comm, theta.data_ptr(), self.P, self.raw.data_ptr())
+                return self.raw
             self.local_eval(theta, self.raw)
             self.comm.allreduce(self.raw.data_ptr(), self.P + 3, self.P, self.epilogue, float(self.n_total))
             return self.raw
         return apply_epilogue(self.eval_raw(theta), self.P, self.epilogue, float(self.n_total))
 
     def eval(self, theta: torch.Tensor):
-        """-> (f, grad) as a python float and a host tensor."""
+        """-> (f, grad) as a python float and a host tensor.  A peer that never arrived (one-shot
+        all-reduce time-out) raises instead of returning the NaN-filled vector."""
         out = self.eval_device(theta).cpu()
+        if self.comm is not None:
+            self.comm.check()
         return float(out[self.P]), out[: self.P].clone()
 
 
@@ -96,4 +104,9 @@ def from_kernel(kernel, workload, device: torch.device, group=None, comm=None) -
         kernel.eval_device(theta.data_ptr(), P, raw.data_ptr(), want_grad=True, apply_epilogue=False)
 
     n_total = int(workload.epilogue_n) if workload.epilogue_n else workload.size
-    return ShardedObjective(local_eval, P, workload.epilogue, n_total, device, group, comm)
+    if device.type == "cuda":
+        # the library launches on the context's stream: make it the stream torch is using on this device,
+        # so the kernel, the collective and the caller's copies of theta / the result are ordered
+        kernel.ctx.use_stream(torch.cuda.current_stream(device).cuda_stream)
+    return ShardedObjective(local_eval, P, workload.epilogue, n_total, device, group, comm,
+                            kernel=kernel if comm is not None else None)

@@ -115,6 +115,11 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_comm_check.argtypes = [c_void_p]
     lib.ad4cl_cuda_comm_destroy.argtypes = [c_void_p]
     lib.ad4cl_cuda_kernel_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_longlong), c_int]
+    lib.ad4cl_cuda_comm_create_local.argtypes = [POINTER(c_void_p), c_int, c_int, POINTER(c_void_p)]
+    lib.ad4cl_cuda_comm_set_timeout.argtypes = [c_void_p, c_double]
+    lib.ad4cl_cuda_eval_sharded.argtypes = [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), c_void_p]
+    lib.ad4cl_cuda_eval_device_sharded.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]
+    lib.ad4cl_cuda_launches_per_eval.argtypes = [c_void_p]
     return lib
 
 
@@ -250,6 +255,27 @@ class Kernel:
         _check(lib.ad4cl_cuda_eval_device(self._h, theta_dev_ptr, nparams, result_dev_ptr,
                                           1 if want_grad else 0, 1 if apply_epilogue else 0))
 
+    def eval_sharded(self, comm: "Comm", theta, want_grad: bool = True):
+        """One sharded evaluation in one call (ad4cl_cuda_eval_sharded): host theta up, ONE kernel whose last
+        CTA all-reduces the raw sums with the peers of `comm` and applies the epilogue, (f, grad) down."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        f = c_double()
+        g = np.empty(len(th)) if want_grad else None
+        _check(lib.ad4cl_cuda_eval_sharded(self._h, comm._h, th.ctypes.data, len(th), byref(f),
+                                           g.ctypes.data if want_grad else None))
+        return f.value, g
+
+    def eval_device_sharded(self, comm: "Comm", theta_dev_ptr: int, nparams: int, result_dev_ptr: int, *,
+                            want_grad: bool = True) -> None:
+        """Device-resident, asynchronous form of eval_sharded: result = [grad..., f, ops, slots] summed over ranks."""
+        _check(lib.ad4cl_cuda_eval_device_sharded(self._h, comm._h, theta_dev_ptr, nparams, result_dev_ptr,
+                                                  1 if want_grad else 0))
+
+    @property
+    def launches_per_eval(self) -> int:
+        """Kernel launches of the last evaluation enqueued (1 unless acc = global)."""
+        return lib.ad4cl_cuda_launches_per_eval(self._h)
+
     def check(self) -> None:
         _check(lib.ad4cl_cuda_check(self._h))
 
@@ -308,10 +334,25 @@ class Kernel:
 class Comm:
     """One-shot NVLink all-reduce of the short result vector (see include/ad4cl_cuda.h)."""
 
-    def __init__(self, ctx: "Context", rank: int, world: int, max_doubles: int):
+    def __init__(self, ctx: "Context", rank: int, world: int, max_doubles: int, _handle=None):
         h = c_void_p()
-        _check(lib.ad4cl_cuda_comm_create(ctx._h, rank, world, max_doubles, byref(h)))
+        if _handle is None:
+            _check(lib.ad4cl_cuda_comm_create(ctx._h, rank, world, max_doubles, byref(h)))
+        else:
+            h = _handle
         self._h, self.rank, self.world = h, rank, world
+
+    @staticmethod
+    def create_local(ctxs: list["Context"], max_doubles: int) -> list["Comm"]:
+        """All ranks in ONE process (one Context per GPU), connected through plain peer access."""
+        n = len(ctxs)
+        arr = (c_void_p * n)(*[c._h for c in ctxs])
+        out = (c_void_p * n)()
+        _check(lib.ad4cl_cuda_comm_create_local(arr, n, max_doubles, out))
+        return [Comm(ctxs[r], r, n, max_doubles, _handle=c_void_p(out[r])) for r in range(n)]
+
+    def set_timeout(self, seconds: float) -> None:
+        _check(lib.ad4cl_cuda_comm_set_timeout(self._h, float(seconds)))
 
     def handle(self) -> bytes:
         buf = ctypes.create_string_buffer(lib.ad4cl_cuda_comm_handle_bytes())

@@ -416,9 +416,7 @@ def main():
             "config": dict(config, ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
                            l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
-                           tape_tier=args.tape, acc_mode=args.acc,
-                           sweep_prefetch={1: "on", 0: "off"}.get(stats.get("sweep_prefetch"), "undecided")
-                           + (" (auto-tuned on the first evaluation)" if args.prefetch == "auto" else "")),
+                           tape_tier=args.tape, acc_mode=args.acc),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     # N = 1: ad4cl_cuda_eval moves P host-packed ad_variables (16 B each) up and P+4 doubles down;
                     # N > 1: P doubles up, the all-reduced P+3 doubles down
@@ -427,7 +425,9 @@ def main():
                     "note": "observations device-resident across evaluations as in simple.cpp:206-230; "
                             "theta up / [grad,f,ops,slots(,status)] down every step",
                     "with_data_upload": e2e_cold},
-            "gpu_launches": (4 if comm is not None else 3) * K, "clocks": clocks, "roofline": roofline,
+            # one launch per evaluation: packing, record + sweep, both reduction stages, all-reduce and epilogue
+            # happen inside the user kernel's entry (NCCL mode adds torch's collective + epilogue kernels)
+            "gpu_launches": k.launches_per_eval * K, "clocks": clocks, "roofline": roofline,
             "ad_ops_per_s": float(st_result[P + 1]) * value,
             "objective": float(st_result[P])}
 

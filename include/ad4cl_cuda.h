@@ -72,10 +72,9 @@ enum {
     AD4CL_TAPE_SHARED = 1   /* rows in shared memory (short tapes) */
 };
 
-/* L2 prefetch of tape rows two batches ahead in the sweep.  Helps a latency-bound evaluation
-   (catch-at-age: +6 %), costs a bandwidth-bound one up to 5 % (tape_stress); results are
-   bit-identical either way.  AUTO times both settings on the first gradient evaluation of a
-   configured kernel (two to four extra evaluations, once) and keeps the faster. */
+/* Round 1: L2 prefetch of tape rows in the sweep, auto-tuned.  Since round 2 the tape of a warp is a
+   warp-uniform header stream plus per-lane cells (ad4cl_tape.cuh): short tapes stay L2 resident and
+   long ones stream at the HBM rate, so the option is accepted for compatibility and ignored. */
 enum {
     AD4CL_PREFETCH_AUTO = -1,
     AD4CL_PREFETCH_OFF = 0,
@@ -101,7 +100,7 @@ typedef struct ad4cl_kernel_config {
     double epilogue_n;         /* n of the epilogue; 0 = number of data work-items */
     int blocks_per_sm;         /* persistent grid = SMs x this; 0 = occupancy maximum */
     int reference_quirks;      /* builtin kernels only: 1 = reference arithmetic as written */
-    int sweep_prefetch;        /* AD4CL_PREFETCH_*: L2 prefetch of tape rows in the sweep (never changes a result bit) */
+    int sweep_prefetch;        /* AD4CL_PREFETCH_*: accepted and ignored since round 2 */
 } ad4cl_kernel_config;
 
 typedef struct ad4cl_eval_stats {
@@ -111,7 +110,7 @@ typedef struct ad4cl_eval_stats {
     size_t smem_bytes;
     size_t arena_bytes;
     float kernel_ms;        /* device time of the last evaluation (both launches) */
-    int sweep_prefetch;     /* the setting in use: 0 off, 1 on, -1 not decided yet (AD4CL_PREFETCH_AUTO before the first gradient evaluation) */
+    int sweep_prefetch;     /* always 0 since round 2 */
 } ad4cl_eval_stats;
 
 int ad4cl_cuda_init(int device, ad4cl_context** ctx);
@@ -187,10 +186,10 @@ int ad4cl_cuda_eval(ad4cl_kernel* kernel, const double* theta, int nparams, doub
  * nparams+3 doubles [grad..., S_or_f, ops, slots].  With apply_epilogue = 0 the
  * raw sums are left (so partial results of several devices can be added before
  * the epilogue is applied).  Errors raised by the launch itself surface at the
- * next ad4cl_cuda_check().  With sweep_prefetch = AD4CL_PREFETCH_AUTO the FIRST gradient
- * evaluation of a configured kernel first runs two to four timed evaluations and
- * synchronises the stream (not while the stream is being captured into a CUDA graph:
- * then the prefetch stays off until a later, uncaptured call).
+ * next ad4cl_cuda_check().  ONE kernel launch per call: parameter packing, record + sweep,
+ * both reduction stages and the epilogue run inside the user kernel's entry (with
+ * AD4CL_ACC_GLOBAL, i.e. the matrix configs, packing and the second stage are separate
+ * small launches).  Capturable into a CUDA graph.
  */
 int ad4cl_cuda_eval_device(ad4cl_kernel* kernel, const double* theta_dev, int nparams,
         double* result_dev, int want_gradient, int apply_epilogue);
@@ -276,12 +275,35 @@ int ad4cl_cuda_measure_fp64_peak(ad4cl_context* ctx, double* tflops);
  *   check    synchronise and report a peer that never arrived
  */
 int ad4cl_cuda_comm_create(ad4cl_context* ctx, int rank, int world, int max_doubles, ad4cl_comm** comm);
+/* all `world` ranks in ONE process (a C++ host driving every GPU of the box, examples/main_cuda.cpp):
+   contexts of distinct devices, peers reached by plain peer access, no handle exchange; comms_out
+   receives `world` connected communicators, rank r on ctxs[r] */
+int ad4cl_cuda_comm_create_local(ad4cl_context** ctxs, int world, int max_doubles, ad4cl_comm** comms_out);
+/* how long a rank waits for its peers before the evaluation fails (default 30 s).  A timed-out
+   all-reduce leaves NaN in the reduced vector, ad4cl_cuda_eval_sharded / _comm_check return an error,
+   and the communicator must be destroyed and rebuilt (its epochs are no longer aligned). */
+int ad4cl_cuda_comm_set_timeout(ad4cl_comm* comm, double seconds);
 int ad4cl_cuda_comm_handle_bytes(void);
 int ad4cl_cuda_comm_handle(ad4cl_comm* comm, void* handle_out);
 int ad4cl_cuda_comm_connect(ad4cl_comm* comm, const void* handles);
 int ad4cl_cuda_comm_allreduce(ad4cl_comm* comm, double* data_dev, int n, int nparams, int epilogue, double n_obs);
 int ad4cl_cuda_comm_check(ad4cl_comm* comm);
 int ad4cl_cuda_comm_destroy(ad4cl_comm* comm);
+/*
+ * One SHARDED evaluation in one call (SURVEY.md 8(b) `..._eval_sharded`): `kernel` is bound to this
+ * rank's shard of the observations; theta (host, nparams doubles, the same on every rank) goes up,
+ * the kernel's last CTA all-reduces the raw sums [grad, S, ops, slots] with the peers of `comm` over
+ * NVLink and applies the epilogue, f and grad[nparams] (identical bits on every rank) come down.
+ * Replayed as ONE CUDA graph: H2D, one kernel, D2H.  Every rank of the communicator must call it
+ * the same number of times.  _device_ form: theta and result ([grad, f, ops, slots]) stay in device
+ * memory, asynchronous on the context's stream.
+ */
+int ad4cl_cuda_eval_sharded(ad4cl_kernel* kernel, ad4cl_comm* comm, const double* theta, int nparams,
+        double* f, double* grad);
+int ad4cl_cuda_eval_device_sharded(ad4cl_kernel* kernel, ad4cl_comm* comm, const double* theta_dev, int nparams,
+        double* result_dev, int want_gradient);
+/* kernel launches the last evaluation of this kernel enqueued (1 unless AD4CL_ACC_GLOBAL) */
+int ad4cl_cuda_launches_per_eval(ad4cl_kernel* kernel);
 
 #ifdef __cplusplus
 }
