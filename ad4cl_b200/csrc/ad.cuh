@@ -134,7 +134,7 @@ AD4CL_DEV void pad_init(int operations, struct ad_gradient_structure* pgs,
 AD4CL_DEV void ad_init_var_g(struct ad_gradient_structure* gs, struct ad_variable* var, double value) {
     var->value = value;
     if (gs->recording == 1) {
-        ad4cl::tape_push<1>(gs->tape, 0.0, 0, ad4cl::kEndFlag | ad4cl::kNopFlag, ad4cl::kNoId);
+        ad4cl::tape_push<1>(gs->tape, 0.0, 0, ad4cl::kEndFlag | ad4cl::kNopFlag);
         var->id = ad4cl::tape_close_op(gs->tape);
         gs->counter++;
     } else {
@@ -151,8 +151,7 @@ namespace ad4cl {
 template <int UA>
 AD4CL_DEV int record1(struct ad_gradient_structure* gs, double dx, int id) {
     ThreadTape* t = gs->tape;
-    const int prev = t->next_id - 1; /* id of the previous operator's result */
-    tape_push<UA>(t, dx, id, kEndFlag, prev);
+    tape_push<UA>(t, dx, id, kEndFlag);
     const int r = tape_close_op(t);
     gs->counter++;
     return r;
@@ -161,9 +160,7 @@ AD4CL_DEV int record1(struct ad_gradient_structure* gs, double dx, int id) {
 template <int UA, int UB>
 AD4CL_DEV int record2(struct ad_gradient_structure* gs, double dx0, int id0, double dx1, int id1) {
     ThreadTape* t = gs->tape;
-    const int prev = t->next_id - 1;
-    tape_push<UA>(t, dx0, id0, 0, prev);
-    tape_push<UB>(t, dx1, id1, kEndFlag, prev);
+    tape_push2<UA, UB>(t, dx0, id0, dx1, id1);
     const int r = tape_close_op(t);
     gs->counter++;
     return r;

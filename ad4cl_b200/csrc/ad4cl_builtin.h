@@ -14,4 +14,5 @@ struct ad4cl_static_row {
     int nparams;
     int frozen_arg;
     int frozen_value;
+    int slots;      /* operand slots one work-item records: the instance is only chosen when the configured tape holds them */
 };

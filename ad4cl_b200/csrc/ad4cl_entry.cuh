@@ -66,6 +66,15 @@ struct LaunchInfo {
     int epilogue;           /* 1: f = (n/2) log S, grad *= (n/2) / S  (simple.cpp:365) */
     double n_obs;
     CommInfo comm;          /* world > 1: the last CTA also all-reduces the raw sums with the peers */
+    /* ---- general epilogues: f = h(out_1 .. out_n) in two passes, nothing retained.
+       Pass 1 (out_values set, objective only): every work-item stores out_i.value.  The caller turns them
+       into seeds s_i = dh/d out_i.  Pass 2 (seeds set): the sweep of work-item i starts from s_i instead of 1,
+       so the reduced gradient is sum_i s_i * d out_i / d theta.  Both indexed like the kernel's own out[]. */
+    const double* seeds;
+    double* out_values;
+    long long n_user;       /* work-items the caller configured (the NDRange is padded to whole work-groups) */
+    const int* skip;        /* non-null: the evaluation is skipped when *skip != 0 at execution time (a device-side
+                               predicate: evaluations captured in a CUDA graph after an optimiser has converged) */
 };
 
 /* Per-thread NDRange coordinates, published for get_global_id() and friends. */
@@ -75,6 +84,12 @@ struct ItemIds {
 
 #ifndef AD4CL_MAX_BLOCK
 #define AD4CL_MAX_BLOCK 256
+#endif
+/* 1: the user kernel synchronises its work-group (barrier()): it cannot be re-run by a single warp, so
+   the entry is built with the general recorder only (the shim defines this for JIT kernels whose text
+   contains a barrier; none of the built-in kernels has one) */
+#ifndef AD4CL_BODY_HAS_BARRIER
+#define AD4CL_BODY_HAS_BARRIER 0
 #endif
 
 __shared__ ItemIds ad4cl_item_ids[AD4CL_MAX_BLOCK];
@@ -231,6 +246,7 @@ __device__ __forceinline__ void finish_evaluation(const LaunchInfo& L, int ncols
  */
 template <int RECORDING, typename Body>
 __device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&& body) {
+    if (L.skip != nullptr && *reinterpret_cast<const volatile int*> (L.skip) != 0) return;
     constexpr int P = AD4CL_P;
     constexpr int ncols = P + 3;
     const int B = blockDim.x;
@@ -268,7 +284,8 @@ __device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&&
         const int gid1 = grp1 * l1 + tid / L.l0;
         ad4cl_item_ids[tid].gid0 = gid0;
         ad4cl_item_ids[tid].gid1 = gid1;
-        const long long out_index = (long long) gid1 * L.g0_user + gid0;
+        /* the register-tier instances are 1-D kernels (the shim checks): out[get_global_id(0)] */
+        const long long out_index = gid0;
 
         struct ad_gradient_structure gs;
         gs.gradient_stack = nullptr;
@@ -282,7 +299,10 @@ __device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&&
         struct ad_variable outv = {0.0, kNoId};
         body(&gs, &outv - out_index, th);
         sum += outv.value;
-        if (RECORDING == 1 && tape.status == kOk) tape_sweep_static(tape, outv.id, g);
+        const bool mine = gid0 < L.g0_user && out_index < L.n_user;
+        if (L.out_values != nullptr && mine) L.out_values[out_index] = outv.value;
+        const double seed = L.seeds == nullptr ? 1.0 : (mine ? L.seeds[out_index] : 0.0);
+        if (RECORDING == 1 && tape.status == kOk) tape_sweep_static(tape, outv.id, g, seed);
         total_ops += tape.nops;
         total_slots += tape.next_id - P;
         status |= tape.status;
@@ -327,6 +347,7 @@ __device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&&
 #else
 template <int MODE, typename Body>
 __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) {
+    if (L.skip != nullptr && *reinterpret_cast<const volatile int*> (L.skip) != 0) return;
     const int B = blockDim.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -384,6 +405,11 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     T.global_acc = L.global_grad;
 
     double sum = 0.0;
+    PendingParam pend = {0.0, -1};
+    /* Which recorder a work-item starts with is decided per warp: the optimistic uniform recorder
+       until it failed for 3 work-items in a row (a kernel with lane-dependent parameter ids or divergent
+       control flow), then the general one for good.  Warp-uniform by construction (set from votes). */
+    int opt_fails = 0;
     const long long ngroups = (L.n_items + B - 1) / B;
     const int groups0 = L.g0 / L.l0;           /* work-groups along dimension 0 */
     const int l1 = B / L.l0;
@@ -410,30 +436,54 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         gs.tape = &tape;
 
         struct ad_variable outv = {0.0, kNoId};
-        body(&gs, &outv - out_index);
-        sum += outv.value;
-        if (L.retain_meta != nullptr) { /* tape export: leave the rows in the arena for the host */
-            double* m = L.retain_meta + 3 * item;
-            m[0] = outv.value;
-            m[1] = (double) outv.id;
-            m[2] = (double) (tape.next_id - tape.first_temp);
-            continue;
-        }
-        /* a thread whose tape overflowed skips the sweep (the host reports the error) */
-        if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
-            /* ONE vote: every lane recorded every row uniformly and all lanes seed the same id */
+        const bool mine = gid0 < L.g0_user && out_index < L.n_user;
+        const double seed = L.seeds == nullptr ? 1.0 : (mine ? L.seeds[out_index] : 0.0);
+        bool general = true;
+#if !AD4CL_BODY_HAS_BARRIER && !AD4CL_FORCE_GENERAL
+        general = opt_fails >= 3 || L.recording != 1 || L.retain_meta != nullptr;
+        if (!general) {
+            /* ---- first copy of the user kernel: the uniform recorder ---- */
+            tape_begin(tape, kRecordUniform);
+            body(&gs, &outv - out_index);
+            /* ONE vote: no lane saw anything the uniform recorder cannot take, and all lanes seed the same id */
             int same = 0;
-            __match_all_sync(0xffffffffu, tape_is_uniform(tape) ? outv.id : -2 - lane, &same);
+            __match_all_sync(0xffffffffu, tape.bad ? 0xffffffff00000000ull + (unsigned) lane : tape_uniform_key(tape, outv.id), &same);
+            /* classify the rows (once per row for the whole warp); a far operand without a far plane is the
+               one thing it can still refuse */
+            if (same && tape_classify_uniform(tape.hdr, tape.far_adj, tape.next_id - tape.first_temp, tape.first_temp, tape.wm1)) same = 0;
             if (same) {
-                tape_sweep_uniform<MODE>(tape, outv.id, T);
+                opt_fails = 0;
+                tape_sweep_uniform<MODE>(tape, outv.id, seed, T, pend);
             } else {
-                tape.status |= tape_sweep_general<MODE>(tape.hdr, tape.cells, tape.lane_words, tape.far_adj,
-                        tape.next_id - tape.first_temp, tape.first_temp, tape.wm1, outv.id, T,
+                opt_fails++;
+                general = true;
+                outv.value = 0.0;
+                outv.id = kNoId;
+                gs.counter = 0;
+            }
+        }
+#endif
+        if (general) {
+            /* ---- second copy: the general recorder (also: objective only, tape export) ---- */
+            tape_begin(tape, kRecordGeneral);
+            body(&gs, &outv - out_index);
+            if (L.retain_meta != nullptr) { /* tape export: leave the rows in the arena for the host */
+                double* m = L.retain_meta + 3 * item;
+                m[0] = outv.value;
+                m[1] = (double) outv.id;
+                m[2] = (double) (tape.next_id - tape.first_temp);
+            } else if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
+                /* a thread whose tape overflowed skips the sweep (the host reports the error) */
+                tape.status |= tape_sweep_general<MODE>(tape.cells, tape.lane_words, tape.far_adj,
+                        tape.next_id - tape.first_temp, tape.first_temp, tape.wm1, outv.id, seed, T,
                         (int) L.cap_slots + kGuardRows);
             }
         }
+        sum += outv.value;
+        if (L.out_values != nullptr && mine) L.out_values[out_index] = outv.value;
         tape_rewind(tape);
     }
+    if (MODE == kAccWarp) param_flush(T.warp_acc, pend);
 
     /* ---- block reduction: warp shuffles, then warps in fixed order ---- */
     __syncthreads();
@@ -515,7 +565,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK)                           \
     AD4CL_STATIC_ENTRY_NAME(NAME)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
         auto body = [&](struct ad_gradient_structure* gs, struct ad_variable* out,         \
-                struct ad_variable* th) {                                                  \
+                struct ad_variable* th) __attribute__((always_inline)) {                   \
             struct ad_entry* gradient_stack = nullptr;                                     \
             (void) gradient_stack; (void) th;                                              \
             NAME(AD4CL_UNPAREN ARGS);                                                      \
@@ -528,7 +578,10 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 #define AD4CL_OBJECTIVE_ENTRY_MODE(NAME, MODE, PARAMS, ARGS)                               \
     extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK, AD4CL_MIN_BLOCKS)        \
     AD4CL_ENTRY_NAME(NAME, MODE)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
-        ad4cl::run_objective<MODE>(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out) { \
+        /* always_inline: the body is instantiated twice (uniform and general recorder), and only inlined  \
+           copies let the compiler keep the tape cursor in registers and fold the recorder mode */        \
+        ad4cl::run_objective<MODE>(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out)      \
+                __attribute__((always_inline)) {                                           \
             struct ad_entry* gradient_stack = nullptr;                                     \
             (void) gradient_stack;                                                         \
             NAME(AD4CL_UNPAREN ARGS);                                                      \

@@ -57,24 +57,20 @@ namespace ad4cl {
  *   [29] PARAM    operand is an independent; payload = its id
  *   [28] FAR      operand is a temporary W or more slots old; payload = its position
  *   [27] HAS_FAR  (END slots) the result of this operator received FAR contributions
- *   [26] CHAIN    operand is the result of the immediately preceding operator
- *   [25:0] payload
+ *   [26:0] payload
  */
 constexpr int kEndFlag = (int) 0x80000000u;
 constexpr int kNopFlag = 0x40000000;
 constexpr int kParamFlag = 0x20000000;
 constexpr int kFarFlag = 0x10000000;
 constexpr int kHasFarFlag = 0x08000000;
-constexpr int kChainFlag = 0x04000000;
-constexpr int kIdMask = 0x03FFFFFF;
+constexpr int kIdMask = 0x07FFFFFF;
 /* "no output written" / not a variable.  INT_MIN, not -1: as an operand it fails the push's one unsigned
    reach test for every row index (ad_plus_eq_g on the virtual out before it was assigned) and is then
    recorded as a constant by tape_classify_rare. */
 constexpr int kNoId = (int) 0x80000000u;
 
-/* second header word: byte offset of the slot's cell in the lane's cell column (a multiple of 256) | flags */
-constexpr unsigned kAuxNonUniform = 1u;     /* the row is not warp-uniform: id word in the lane-word plane, cell always own */
-constexpr unsigned kAuxOffsetMask = ~255u;
+/* second header word (uniform recorder): byte offset of the slot's cell in the lane's cell column */
 
 constexpr int kHdrBytes = 8;
 constexpr int kCellRowBytes = 256;          /* 32 lanes x 8 B */
@@ -98,10 +94,11 @@ enum Status : int {
 #ifndef AD4CL_DEBUG_BOUNDS
 #define AD4CL_DEBUG_BOUNDS 0
 #endif
-/* A/B switch (make general -> libad4cl_cuda_general.so, tests/test_gpu_format_ab.py): 1 records every
-   row as non-uniform, i.e. the per-lane format and the general sweep everywhere.  Every lane then
-   performs the same floating-point operations in the same order as in the uniform format, so the
-   results are bit-identical by construction. */
+/* A/B switch (make general -> libad4cl_cuda_general.so, tests/test_gpu_format_ab.py): 1 never tries the
+   uniform recorder, i.e. the per-lane format and the general sweep everywhere.  Per lane the tape
+   arithmetic is the same in both formats; only the order in which an independent's contributions are
+   summed over the warp differs (pairs in the uniform sweep), so results agree to rounding, and bit for
+   bit with per-thread accumulators. */
 #ifndef AD4CL_FORCE_GENERAL
 #define AD4CL_FORCE_GENERAL 0
 #endif
@@ -164,6 +161,12 @@ __host__ __device__ inline size_t warp_region_bytes(unsigned cap_slots, bool far
 #ifndef AD4CL_TAPE_STATIC
 #define AD4CL_TAPE_STATIC 0
 #endif
+/* 1: the uniform recorder checks warp-uniformity with per-lane hashes compared once per work-item instead
+   of a MATCH.ALL vote per push (exact vs 2^-64; measured variant, see profiles/README.md).  Default 0. */
+#ifndef AD4CL_UNIFORM_HASH
+#define AD4CL_UNIFORM_HASH 0
+#endif
+
 
 #if AD4CL_TAPE_STATIC
 /*
@@ -208,8 +211,7 @@ __device__ __forceinline__ void tape_bind_static(ThreadTape& t) {
 }
 
 template <int UNIT>
-__device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags, int prev_id) {
-    (void) prev_id;
+__device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
     const int n = t->next_id - AD4CL_P;
     int word;
     if (flags & kNopFlag) word = flags;
@@ -223,6 +225,12 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
         t->status |= kErrTapeOverflow;
     }
     t->next_id++;
+}
+
+template <int UA, int UB>
+__device__ __forceinline__ void tape_push2(ThreadTape* t, double dx0, int id0, double dx1, int id1) {
+    tape_push<UA>(t, dx0, id0, 0);
+    tape_push<UB>(t, dx1, id1, kEndFlag);
 }
 
 __device__ __forceinline__ int tape_close_op(ThreadTape* t) {
@@ -293,48 +301,60 @@ struct StaticSweep<0> {
 
 /* Reverse sweep of the register tape into per-thread accumulators g[AD4CL_P] (ad4cl.h:786-797 on the
    slot stream).  With compile-time id words every adj[] / g[] index is a constant. */
-__device__ __forceinline__ void tape_sweep_static(const ThreadTape& t, int out_id, double (&g)[AD4CL_P > 0 ? AD4CL_P : 1]) {
+__device__ __forceinline__ void tape_sweep_static(const ThreadTape& t, int out_id, double (&g)[AD4CL_P > 0 ? AD4CL_P : 1], double seed) {
     const int n = t.next_id - AD4CL_P;
     double adj[AD4CL_STATIC_SLOTS];
     StaticIndex<AD4CL_STATIC_SLOTS>::zero(adj);
-    if ((unsigned) out_id < (unsigned) AD4CL_P) StaticIndex<(AD4CL_P > 0 ? AD4CL_P : 1)>::add(g, out_id, 1.0);
-    else if (out_id - AD4CL_P < n) StaticIndex<AD4CL_STATIC_SLOTS>::set(adj, out_id - AD4CL_P, 1.0);
+    if ((unsigned) out_id < (unsigned) AD4CL_P) StaticIndex<(AD4CL_P > 0 ? AD4CL_P : 1)>::add(g, out_id, seed);
+    else if (out_id - AD4CL_P < n) StaticIndex<AD4CL_STATIC_SLOTS>::set(adj, out_id - AD4CL_P, seed);
     double w = 0.0;
     StaticSweep<AD4CL_STATIC_SLOTS>::run(t, n, w, adj, g);
 }
 
 #else /* !AD4CL_TAPE_STATIC: the arena / shared-memory tape */
 
+/*
+ * Two recorders share the planes of a warp's region; which one a push uses is `mode`, a literal in each
+ * of the two inlined copies of the user kernel (ad4cl_entry.cuh), so a push contains only its own code.
+ *
+ *   kRecordUniform  OPTIMISTIC: assumes all 32 lanes push the same id word at the same row and the
+ *                   operand is an independent or a recent temporary.  One header per warp, a cell only
+ *                   for a non-unit partial.  Nothing is branched on: whatever breaks the assumption
+ *                   (partial mask, lane-dependent id word, far or foreign operand, full column) only
+ *                   sets the sticky `bad` flag, and the work-item is then recorded AGAIN by the general
+ *                   recorder.  Re-running the user kernel is safe because its only effects are the tape
+ *                   and the virtual out (kernels with work-group barriers are built general-only).
+ *   kRecordGeneral  every lane keeps its own id word (lane-word plane, 128 B per row) and its own
+ *                   partial (cell row + 2): any control flow, any ids, far operands.
+ */
+constexpr int kRecordUniform = 0;
+constexpr int kRecordGeneral = 1;
+
 struct ThreadTape {
+    int mode;             /* kRecordUniform / kRecordGeneral */
     char* hdr;            /* header plane of this warp, row 0 (the same address in all lanes) */
-    char* hdr_cur;        /* header of the next free row */
+    char* hdr_cur;        /* uniform recorder: header of the next free row */
     char* cells;          /* this lane's cell column: cell k at cells + 256 k */
-    char* lane_words;     /* this lane's id-word column for non-uniform rows: row r at lane_words + 128 r */
+    char* lane_words;     /* this lane's id-word column (general recorder): row r at lane_words + 128 r */
     char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
-    unsigned cell_off;    /* byte offset of this lane's next free cell */
+    unsigned cell_off;    /* uniform recorder: byte offset of this lane's next free cell */
     int next_id;          /* first_temp + index of the next free row */
     int cap_id;           /* first_temp + capacity in slots; kGuardRows guard rows follow */
     int first_temp;       /* number of independents: ids >= first_temp are tape positions */
     int wm1;              /* W - 1, W a power of two >= 4 */
     int nops;             /* operators recorded by the current work-item (statistics) */
-    /* Uniformity vote key of a push = (id word & key_and) | key_or.  While every push of the current
-       work-item was warp-uniform: key_and = ~0, key_or = 0 (the key is the id word; lanes that took
-       part in the same full-mask uniform pushes are at the same row, so the row is not part of the
-       key).  After the first push that was not: key_and = 0, key_or = HAS_FAR | lane -- a value no
-       clean key can have (HAS_FAR is only ever set later, by tape_note_far) and no other lane has, so
-       a lane that diverged never again looks uniform to anybody until the next work-item. */
-    unsigned key_and, key_or;
+    int bad;              /* uniform recorder: sticky "this work-item needs the general recorder" */
+    unsigned h1, h2;      /* AD4CL_UNIFORM_HASH: running hashes of this lane's id words (see tape_push) */
     int status;           /* sticky Status bits */
     long long total_ops;  /* statistics over all work-items of this thread */
     long long total_slots;
 };
 
-__device__ __forceinline__ bool tape_is_uniform(const ThreadTape& t) { return t.key_or == 0u; }
-
 __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsigned cap_slots,
         int first_temp, int window, bool far) {
     const int lane = threadIdx.x & 31;
     const RegionLayout lay = region_layout(cap_slots, far);
+    t.mode = kRecordGeneral;
     t.hdr = warp_region;
     t.hdr_cur = warp_region;
     t.cells = warp_region + lay.off_cells + lane * 8;
@@ -346,129 +366,187 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
     t.first_temp = first_temp;
     t.wm1 = window - 1;
     t.nops = 0;
-    t.key_and = ~0u;
-    t.key_or = 0u;
+    t.bad = 0;
+    t.h1 = t.h2 = 0u;
     t.status = kOk;
     t.total_ops = 0;
     t.total_slots = 0;
-    /* the two constant cells every unit slot points at */
+    /* the two constant cells every unit slot of the uniform recorder points at */
     *reinterpret_cast<double*> (t.cells) = 1.0;
     *reinterpret_cast<double*> (t.cells + kCellRowBytes) = -1.0;
 }
 
+/* Start recording a work-item (or start over, after a failed optimistic attempt). */
+__device__ __forceinline__ void tape_begin(ThreadTape& t, int mode) {
+    t.mode = mode;
+    t.hdr_cur = t.hdr;
+    t.cell_off = kUnitCells * kCellRowBytes;
+    t.next_id = t.first_temp;
+    t.nops = 0;
+    t.bad = 0;
+    t.h1 = t.h2 = 0u;
+}
+
+/* What the warp votes on after a work-item recorded by the uniform recorder: equal in all 32 lanes (and
+   no lane `bad`) <=> the work-item is warp-uniform.  With per-push votes (default) only the seed id is left
+   to compare; with AD4CL_UNIFORM_HASH the lanes' running hashes of everything they pushed are compared
+   here instead of their id words at every push. */
+__device__ __forceinline__ unsigned long long tape_uniform_key(const ThreadTape& t, int out_id) {
+#if AD4CL_UNIFORM_HASH
+    return ((unsigned long long) (t.h1 ^ (unsigned) out_id) << 32) | t.h2;
+#else
+    return (unsigned) out_id;
+#endif
+}
+
 /*
- * Rare operand classes, out of line and by value (the tape cursor stays in registers; ~50 push sites
- * per objective would otherwise each carry a copy):
+ * General recorder, rare operand classes, out of line and by value (the tape cursor stays in registers):
  *   - a temporary W or more slots old cannot use the ring: FAR, and HAS_FAR on the END slot of the
- *     operator that produced it -- in the warp's header (read when that row is uniform) and in this
- *     lane's own word (read when it is not).  The far plane is all zeros between work-items (the
- *     sweep restores it), so lanes that see HAS_FAR without having noted anything read a zero.
+ *     operator that produced it.  The far plane is all zeros between work-items (the sweep restores it).
  *   - an id that is neither an independent nor a position below the current row is not a variable of
- *     this tape (the virtual out before it is written, an uninitialised ad_variable): recorded as
- *     a constant operand instead of an id the sweep would follow out of the arena.
+ *     this tape (the virtual out before it is written, an uninitialised ad_variable): recorded as a
+ *     constant operand instead of an id the sweep would follow out of the arena.
  * Returns the id word in the low half and Status bits in the high half.
  */
-static __device__ __noinline__ unsigned long long tape_classify_rare(char* hdr, char* lane_words, const char* far_adj,
+static __device__ __noinline__ unsigned long long tape_classify_rare(char* lane_words, const char* far_adj,
         int id, int first_temp, int row, int flags) {
     const int pos = id - first_temp;
     if (pos < 0 || pos >= row) return (unsigned) (flags | kNopFlag);
     if (far_adj == nullptr) return ((unsigned long long) kErrWindow << 32) | (unsigned) (flags | kNopFlag);
-    atomicOr(reinterpret_cast<int*> (hdr + (size_t) pos * kHdrBytes), kHasFarFlag);
     atomicOr(reinterpret_cast<int*> (lane_words + (size_t) pos * kLaneWordRowBytes), kHasFarFlag);
     return (unsigned) (pos | flags | kFarFlag);
 }
 
-/* The push is not warp-uniform (partial mask, lane-dependent id word, lanes at different rows) or the
-   column is full.  Not uniform: the header only says so, the lane keeps its own id word and always
-   its own cell.  Every lane that passes row r stores the same header (the cell offset is a function
-   of the row index: all rows below r were either uniform for the whole warp or non-uniform for
-   everybody who passed them).  Full: nothing is stored and the sticky overflow bit is returned (the
-   sweep of the work-item is skipped, the host reports AD4CL_ERR_TAPE_OVERFLOW).
-   Returns the new cell offset in the low half and Status bits in the high half. */
-static __device__ __noinline__ unsigned long long tape_push_diverged(char* hdr_cur, char* cells, char* lane_words,
-        int row, int cap_rows, int word, double dx, unsigned cell_off) {
-    if (row >= cap_rows) return ((unsigned long long) kErrTapeOverflow << 32) | cell_off;
-    *reinterpret_cast<int2*> (hdr_cur) = make_int2(0, (int) (cell_off | kAuxNonUniform));
-    *reinterpret_cast<int*> (lane_words + (size_t) row * kLaneWordRowBytes) = word;
-    *reinterpret_cast<double*> (cells + cell_off) = dx;
-    return cell_off + kCellRowBytes;
-}
-
-/* Push one (partial, operand) slot.  `flags` is 0, kEndFlag or kEndFlag|kNopFlag; UNIT = +1 / -1
-   says the partial is the compile-time constant +1.0 / -1.0 (dx is then ignored), 0 a general
-   partial; prev_id is the id of the previous operator's result (CHAIN detection).  The operand is
-   classified here (independent / chained / recent / far temporary) so the sweep only tests flag
-   bits.  The common path -- all 32 lanes push the same id word and the column has room -- is two
-   stores; everything else is one out-of-line call. */
+/*
+ * Push one (partial, operand) slot.  `flags` is 0, kEndFlag or kEndFlag|kNopFlag; UNIT = +1 / -1 says the
+ * partial is the compile-time constant +1.0 / -1.0 (dx is then ignored), 0 a general partial.
+ *
+ * Uniform recorder: the header gets the RAW word id | flags.  Everything a lane does here is the vote
+ * (same raw word in all 32 lanes, full mask), two cheap sanity tests (the id names a variable that exists:
+ * id < next_id; the column has room) folded into the sticky `bad`, two stores and the cursor bumps.
+ * Classifying the operand (independent / recent / far temporary) is NOT done per lane and per push: the
+ * structure is warp-uniform, so tape_classify_uniform does it once per ROW, the rows dealt out over the lanes.
+ *
+ * General recorder: the operand is classified here, per lane.
+ */
 template <int UNIT>
-__device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags, int prev_id) {
-    int word;
-    if (flags & kNopFlag) {
-        word = flags;  /* a leaf: no operand */
+__device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
+    if (t->mode == kRecordUniform) {
+        const int word = (flags & kNopFlag) ? flags : (id | flags);
+        const bool valid = (flags & kNopFlag) || (unsigned) id < (unsigned) t->next_id;
+        const bool room = t->next_id < t->cap_id;
+#if AD4CL_UNIFORM_HASH
+        /* no vote per push: every lane folds its raw word into two independent multiplicative hashes and the
+           warp compares them ONCE per work-item (tape_uniform_key).  A lane that skipped a push, pushed in
+           another order or pushed another word ends with different hashes, up to a 2^-64 collision. */
+        t->h1 = t->h1 * 0x9E3779B1u + (unsigned) word;
+        t->h2 = (t->h2 ^ (unsigned) word) * 0x85EBCA6Bu + 0xC2B2AE35u;
+        t->bad |= (!valid || !room) ? 1 : 0;
+#else
+        const unsigned mask = __activemask();
+        int same = 0;
+        __match_all_sync(mask, word, &same);
+        t->bad |= (!valid || !same || mask != 0xffffffffu || !room) ? 1 : 0;
+#endif
+        const unsigned aux = UNIT == 0 ? t->cell_off : (UNIT > 0 ? 0u : (unsigned) kCellRowBytes);
+        *reinterpret_cast<int2*> (t->hdr_cur) = make_int2(word, (int) aux);
+        if (UNIT == 0) *reinterpret_cast<double*> (t->cells + t->cell_off) = dx;
+        if (room) { /* a full column stops advancing (guard rows take the stores); `bad` is already set */
+            t->hdr_cur += kHdrBytes;
+            if (UNIT == 0) t->cell_off += kCellRowBytes;
+        }
+        t->next_id++;
     } else {
         const bool is_param = (unsigned) id < (unsigned) t->first_temp;
-        word = (is_param ? (id | kParamFlag) : (id - t->first_temp)) | flags;
-        if (id == prev_id && !is_param) word |= kChainFlag;
         /* A temporary is within the ring's reach when it is fewer than W - 1 rows below this one (the
-           operator being recorded ends at this row or the next).  One unsigned compare also rejects
-           ids at or above the current row. */
-        const bool near = (unsigned) (t->next_id - 1 - id) < (unsigned) (t->wm1 - 1);
-        if (!is_param && !near) {
-            const unsigned long long r = tape_classify_rare(t->hdr, t->lane_words, t->far_adj, id, t->first_temp,
-                    t->next_id - t->first_temp, flags);
+           operator being recorded ends at this row or the next).  One unsigned compare also rejects ids
+           at or above the current row and kNoId. */
+        const bool reach = (unsigned) (t->next_id - 1 - id) < (unsigned) (t->wm1 - 1);
+        int word = (flags & kNopFlag) ? flags : (is_param ? (id | kParamFlag) : (id - t->first_temp)) | flags;
+        const bool room = t->next_id < t->cap_id;
+        const int row = t->next_id - t->first_temp;
+        if (!(flags & kNopFlag) && !is_param && !reach) {
+            const unsigned long long r = tape_classify_rare(t->lane_words, t->far_adj, id, t->first_temp, row, flags);
             word = (int) (unsigned) r;
             t->status |= (int) (r >> 32);
         }
+        *reinterpret_cast<double*> (t->cells + (size_t) (row + kUnitCells) * kCellRowBytes) = UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0);
+        *reinterpret_cast<int*> (t->lane_words + (size_t) row * kLaneWordRowBytes) = word;
+        /* a full column stays on its guard row and says so (the sweep is skipped, the host reports it) */
+        t->status |= room ? kOk : kErrTapeOverflow;
+        t->next_id += room ? 1 : 0;
     }
-    const unsigned mask = __activemask();
-    int same = 0;
-    __match_all_sync(mask, ((unsigned) word & t->key_and) | t->key_or, &same);
-    if (!AD4CL_FORCE_GENERAL && same && mask == 0xffffffffu && t->next_id < t->cap_id) {
-        const unsigned aux = UNIT == 0 ? t->cell_off : (UNIT > 0 ? 0u : (unsigned) kCellRowBytes);
-        *reinterpret_cast<int2*> (t->hdr_cur) = make_int2(word, (int) aux);
-        if (UNIT == 0) {
-            *reinterpret_cast<double*> (t->cells + t->cell_off) = dx;
-            t->cell_off += kCellRowBytes;
-        }
-    } else {
-        const unsigned long long r = tape_push_diverged(t->hdr_cur, t->cells, t->lane_words, t->next_id - t->first_temp,
-                t->cap_id - t->first_temp, word, UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0), t->cell_off);
-        t->cell_off = (unsigned) r;
-        t->status |= (int) (r >> 32);
-        t->key_and = 0u;
-        t->key_or = (unsigned) kHasFarFlag | (threadIdx.x & 31u);
-    }
-    t->hdr_cur += kHdrBytes;
-    t->next_id++;
 }
 
-/* Close the operator whose slots were just pushed; returns its result id (the position of its END
-   slot).  Capacity is checked by the pushes themselves. */
+/*
+ * Uniform recorder, after the work-item: turn the raw words id | flags of the `rows` headers into the
+ * classified id words the sweep reads (PARAM + id; position of a recent temporary; FAR + position, with
+ * HAS_FAR -- one byte store into the low byte of the producer's cell offset, which is always 0 -- on the row
+ * that produced the operand).  ONE classification per row for the whole warp, row r by lane r mod 32.
+ * Returns non-zero (warp-uniform) when the tape needs the general recorder after all: a far operand with the
+ * far plane disabled.  Out of line: runs once per work-item.
+ */
+static __device__ __noinline__ int tape_classify_uniform(char* hdr, const char* far_adj, int rows, int first_temp, int wm1) {
+    int bad = 0;
+    for (int r = threadIdx.x & 31; r < rows; r += 32) {
+        int* hw = reinterpret_cast<int*> (hdr + (size_t) r * kHdrBytes);
+        const int raw = *hw;
+        const int flags = raw & (kEndFlag | kNopFlag);
+        const int id = raw & kIdMask;
+        int word = flags;
+        if (!(flags & kNopFlag)) {
+            if (id < first_temp) {
+                word = id | kParamFlag | flags;
+            } else {
+                const int pos = id - first_temp;
+                word = pos | flags;
+                if (!((unsigned) (first_temp + r - 1 - id) < (unsigned) (wm1 - 1))) { /* beyond the ring's reach */
+                    if (far_adj == nullptr) {
+                        bad = 1;
+                    } else {
+                        word |= kFarFlag;
+                        *reinterpret_cast<unsigned char*> (hdr + (size_t) pos * kHdrBytes + 4) = 1;
+                    }
+                }
+            }
+        }
+        *hw = word;
+    }
+    __syncwarp();
+    return __any_sync(0xffffffffu, bad);
+}
+
+/* Both slots of a two-operand operator. */
+template <int UA, int UB>
+__device__ __forceinline__ void tape_push2(ThreadTape* t, double dx0, int id0, double dx1, int id1) {
+    tape_push<UA>(t, dx0, id0, 0);
+    tape_push<UB>(t, dx1, id1, kEndFlag);
+}
+
+/* Close the operator whose slots were just pushed; returns its result id (the position of its END slot). */
 __device__ __forceinline__ int tape_close_op(ThreadTape* t) {
     t->nops++;
     return t->next_id - 1;
 }
 
-/* Forget the current work-item's tape (the arena column is reused). */
+/* The work-item is done: fold its counts into the statistics (the arena column is reused). */
 __device__ __forceinline__ void tape_rewind(ThreadTape& t) {
     t.total_ops += t.nops;
     t.total_slots += t.next_id - t.first_temp;
-    t.hdr_cur = t.hdr;
-    t.cell_off = kUnitCells * kCellRowBytes;
     t.next_id = t.first_temp;
     t.nops = 0;
-    t.key_and = ~0u;
-    t.key_or = 0u;
 }
 
-/* Debug / export accessor: id word (CHAIN stripped) and partial of row `row` of this lane's tape. */
+/* Debug / export accessor: id word and partial of row `row` of this lane's tape. */
 __device__ __forceinline__ void tape_read_row(const ThreadTape* t, int row, double* dx, int* word) {
-    const int2 h = *reinterpret_cast<const int2*> (t->hdr + (size_t) row * kHdrBytes);
-    const unsigned aux = (unsigned) h.y;
-    int w = h.x;
-    if (aux & kAuxNonUniform) w = *reinterpret_cast<const int*> (t->lane_words + (size_t) row * kLaneWordRowBytes);
-    *word = w & ~kChainFlag;
-    *dx = *reinterpret_cast<const double*> (t->cells + (aux & kAuxOffsetMask));
+    if (t->mode == kRecordUniform) {
+        const int2 h = *reinterpret_cast<const int2*> (t->hdr + (size_t) row * kHdrBytes);
+        *word = h.x | ((h.y & 1) << 27);
+        *dx = *reinterpret_cast<const double*> (t->cells + ((unsigned) h.y & ~255u));
+    } else {
+        *word = *reinterpret_cast<const int*> (t->lane_words + (size_t) row * kLaneWordRowBytes);
+        *dx = *reinterpret_cast<const double*> (t->cells + (size_t) (row + kUnitCells) * kCellRowBytes);
+    }
 }
 
 struct SweepTarget {
@@ -515,70 +593,116 @@ __device__ __forceinline__ void sweep_param(const SweepTarget& T, bool is_param,
     }
 }
 
-/* warp-uniform form (uniform sweep): the same independent in all 32 lanes */
+/* Seeds d(out) = seed (1 unless the caller supplied per-work-item seeds) and returns the number of rows
+   the sweep has to visit (rows recorded after `out` are dead; those that could alias the seed's ring
+   entry are dropped). */
 template <int MODE>
-__device__ __forceinline__ void sweep_param_uniform(const SweepTarget& T, int id, double c) {
-    if (MODE == kAccThread) {
-        const unsigned a = T.thread_acc + (unsigned) id * T.stride;
-        sts_f64(a, lds_f64(a) + c);
-    } else if (MODE == kAccWarp) {
-        /* the butterfly of warp_param_reduce with all 32 lanes in one group: same bits */
-        const double v = warp_sum(c);
-        const unsigned a = T.warp_acc + (unsigned) id * 8u;
-        sts_f64(a, lds_f64(a) + v);
-    } else {
-        const double v = warp_sum(c);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&T.global_acc[id], v);
-    }
-}
-
-/* Seeds d(out) = 1 and returns the number of rows the sweep has to visit (rows recorded after `out`
-   are dead; those that could alias the seed's ring entry are dropped). */
-template <int MODE>
-__device__ __forceinline__ int sweep_seed(int rows, int first_temp, int wmask, int out_id, const SweepTarget& T) {
+__device__ __forceinline__ int sweep_seed(int rows, int first_temp, int wmask, int out_id, double seed, const SweepTarget& T) {
     const int seed_pos = out_id - first_temp;
-    sweep_param<MODE>(T, out_id >= 0 && out_id < first_temp, out_id, 1.0);
+    sweep_param<MODE>(T, out_id >= 0 && out_id < first_temp, out_id, seed);
     if (seed_pos >= 0 && seed_pos < rows) {
         if (rows - seed_pos > wmask) rows = seed_pos + wmask;
-        sts_f64(T.ring + ((unsigned) (seed_pos & wmask) << 3), 1.0);
+        sts_f64(T.ring + ((unsigned) (seed_pos & wmask) << 3), seed);
     }
     return rows;
 }
 
 /*
- * Reverse sweep of a work-item whose whole tape was recorded warp-uniformly (the common case): all
- * 32 lanes hold the same rows with the same id words, only the partials differ.  Restates the loop
- * of ad4cl.h:786-797 (w = g[id]; g[id] = 0; g[operand] += w * dx) on the slot stream.
- *
- * Rows are visited in aligned batches of 4 (row 4b+3 down to 4b), software-pipelined two deep and
- * unrolled twice so that no register is ever copied:
- *     headers of batch b-2 (cell offsets)  ->  cells of batch b-1  ->  arithmetic of batch b
- * Header loads are 16-byte broadcasts (the same address in all lanes); a batch's headers are read
- * twice (once for the offsets, once for the id words) instead of being held in registers.
- * All class tests are on warp-uniform values: real branches, no divergence.
+ * kAccWarp in the uniform sweep: contributions to the independents are reduced over the warp TWO AT A
+ * TIME.  A contribution waits in `pend`; when the next one (to another independent) arrives, the lower
+ * half-warp takes over the pending value and the upper half the new one -- one exchange over lane
+ * distance 16 -- and the four remaining butterfly steps reduce both at once: 5 shuffle steps for two
+ * sums instead of 10.  A contribution to the SAME independent as the pending one is just added to it.
+ * The pending contribution survives across work-items and is flushed when the thread's work is done.
+ * The order of the additions is fixed by the tape, so results stay bit-reproducible.
  */
-/* 16-byte generic load of two headers; `volatile` keeps it ONE instruction (the compiler otherwise splits
-   it into the 32-bit loads of the components it needs) and in program order with the other loads */
+struct PendingParam {
+    double c;
+    int id;      /* < 0: nothing pending */
+};
+
+__device__ __forceinline__ void param_flush(unsigned warp_acc, PendingParam& pend) {
+    if (pend.id >= 0) {
+        const double v = warp_sum(pend.c);
+        const unsigned a = warp_acc + (unsigned) pend.id * 8u;
+        sts_f64(a, lds_f64(a) + v);
+        pend.id = -1;
+    }
+}
+
+__device__ __forceinline__ void param_add_paired(unsigned warp_acc, PendingParam& pend, int id, double c) {
+    if (pend.id < 0) {
+        pend.c = c;
+        pend.id = id;
+    } else if (pend.id == id) {
+        pend.c += c;
+    } else {
+        const bool lower = (threadIdx.x & 16u) == 0u;
+        const double mine = lower ? pend.c : c;      /* the sum this half-warp finishes */
+        const double theirs = lower ? c : pend.c;    /* what the other half needs from this lane */
+        double v = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        /* lanes 0-15 hold the pending independent's sum, lanes 16-31 the new one's: two addresses, one
+           read-modify-write instruction (the ids differ, so the two updates cannot collide) */
+        const unsigned a = warp_acc + (unsigned) (lower ? pend.id : id) * 8u;
+        sts_f64(a, lds_f64(a) + v);
+        pend.id = -1;
+    }
+}
+
+/* The far cases of one row of the uniform sweep, out of line and by value: an END row whose result received
+   contributions through the far plane (HAS_FAR) collects them into w; a FAR operand adds w * dx to the far
+   plane entry of its producer.  Returns w. */
+static __device__ __noinline__ double sweep_far_row(char* far_adj, int word, int me, double w, double dx) {
+    if (word < 0 && (word & kHasFarFlag)) {
+        double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
+        w = __dadd_rn(w, *fa);
+        *fa = 0.0;
+    }
+    if (word & kFarFlag) {
+        double* fa = reinterpret_cast<double*> (far_adj + (size_t) (word & kIdMask) * kFarRowBytes);
+        *fa = __dadd_rn(*fa, __dmul_rn(w, dx));
+    }
+    return w;
+}
+
+/* 16-byte generic load of two headers */
 __device__ __forceinline__ int4 ld_hdr2(const void* p) {
     int4 v;
     asm volatile("ld.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
+/*
+ * Reverse sweep of a work-item recorded by the uniform recorder: all 32 lanes hold the same rows with
+ * the same id words, only the partials differ.  Restates the loop of ad4cl.h:786-797 (w = g[id];
+ * g[id] = 0; g[operand] += w * dx) on the slot stream.
+ *
+ * Rows are visited in aligned batches of 4 (row 4b+3 down to 4b), software-pipelined two deep and
+ * unrolled twice so that no register is ever copied:
+ *     headers of batch b-2 (cell offsets)  ->  cells of batch b-1  ->  arithmetic of batch b
+ * Header loads are broadcasts (the same address in all lanes); a batch's headers are read twice (once
+ * for the offsets, once for the id words) instead of being held in registers.  All class tests are
+ * on warp-uniform values: no divergence, and an independent's contribution is reduced over the warp
+ * without any ballot / leader loop.
+ */
 template <int MODE>
 struct UniformSweep {
     const char* hdr;
     const char* cells;
     char* far_adj;
     const SweepTarget& T;
-    int wmask;
-    double w, carry;
+    unsigned wmask8;      /* (W - 1) << 3 */
+    double w;
+    PendingParam& pend;
 
     __device__ __forceinline__ void load_offsets(int b, unsigned (&a)[4]) const {
         if (b >= 0) {
             const char* p = hdr + (size_t) b * (4 * kHdrBytes);
             const int4 x = ld_hdr2(p), y = ld_hdr2(p + 16);
-            a[0] = (unsigned) x.y; a[1] = (unsigned) x.w; a[2] = (unsigned) y.y; a[3] = (unsigned) y.w;
+            a[0] = (unsigned) x.y & ~255u; a[1] = (unsigned) x.w & ~255u;
+            a[2] = (unsigned) y.y & ~255u; a[3] = (unsigned) y.w & ~255u;
         } else {
             a[0] = a[1] = a[2] = a[3] = 0u;
         }
@@ -587,7 +711,9 @@ struct UniformSweep {
         if (b >= 0) {
             const char* p = hdr + (size_t) b * (4 * kHdrBytes);
             const int4 x = ld_hdr2(p), y = ld_hdr2(p + 16);
-            wd[0] = x.x; wd[1] = x.z; wd[2] = y.x; wd[3] = y.z;
+            /* HAS_FAR travels in the low byte of the cell offset (tape_push): fold it into the id word */
+            wd[0] = x.x | ((x.y & 1) << 27); wd[1] = x.z | ((x.w & 1) << 27);
+            wd[2] = y.x | ((y.y & 1) << 27); wd[3] = y.z | ((y.w & 1) << 27);
         } else {
             wd[0] = wd[1] = wd[2] = wd[3] = kNopFlag;
         }
@@ -596,30 +722,33 @@ struct UniformSweep {
 #pragma unroll
         for (int j = 0; j < 4; j++) d[j] = *reinterpret_cast<const double*> (cells + a[j]);
     }
-    /* One row.  Every test is on a warp-uniform value.  The common classes (pop, chained operand,
-       recent temporary) are short predicated sequences; an independent is one real branch around the
-       warp reduction; the two far cases share one rare test. */
     __device__ __forceinline__ void row(int word, double dx, unsigned pop_addr, int me) {
         if (word < 0) { /* END: pop the adjoint of the operator that ends at this slot */
-            w = lds_f64(pop_addr) + carry;
+            w = lds_f64(pop_addr);
             sts_f64(pop_addr, 0.0);
-            carry = 0.0;
         }
-        if (word & (kFarFlag | kHasFarFlag)) { /* rare */
-            if (word < 0 && (word & kHasFarFlag)) { /* contributions that came through the far plane */
-                double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
-                w += *fa;
-                *fa = 0.0;
+        /* the two far cases share ONE test and live out of line: a call on the ~10 % of rows that need it
+           instead of a dozen predicated-off instructions on every row */
+        if (word & (kFarFlag | kHasFarFlag)) w = sweep_far_row(far_adj, word, me, w, dx);
+        /* explicit rounding: the product is never contracted into one of the additions below, so the uniform
+           and the general sweep (and every build) perform the same roundings per lane */
+        const double c = __dmul_rn(w, dx);
+        if ((word & (kNopFlag | kParamFlag | kFarFlag)) == 0) { /* a recent temporary: its ring entry */
+            const unsigned a = T.ring + (((unsigned) word << 3) & wmask8);
+            sts_f64(a, __dadd_rn(lds_f64(a), c));
+        }
+        if (word & kParamFlag) {
+            const int id = word & kIdMask;
+            if (MODE == kAccThread) {
+                const unsigned a = T.thread_acc + (unsigned) id * T.stride;
+                sts_f64(a, __dadd_rn(lds_f64(a), c));
+            } else if (MODE == kAccWarp) {
+                param_add_paired(T.warp_acc, pend, id, c);
+            } else {
+                const double v = warp_sum(c);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&T.global_acc[id], v);
             }
-            if (word & kFarFlag) *reinterpret_cast<double*> (far_adj + (size_t) (word & kIdMask) * kFarRowBytes) += w * dx;
         }
-        const double c = w * dx;
-        if (word & kChainFlag) carry += c;
-        if ((word & (kNopFlag | kParamFlag | kFarFlag | kChainFlag)) == 0) {
-            const unsigned a = T.ring + ((unsigned) (word & wmask) << 3);
-            sts_f64(a, lds_f64(a) + c);
-        }
-        if (word & kParamFlag) sweep_param_uniform<MODE>(T, word & kIdMask, c);
     }
     __device__ __forceinline__ void batch(int b, unsigned rb, const int (&wd)[4], const double (&d)[4]) {
 #pragma unroll
@@ -628,8 +757,8 @@ struct UniformSweep {
 };
 
 template <int MODE>
-__device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, const SweepTarget& T) {
-    int rows = sweep_seed<MODE>(t.next_id - t.first_temp, t.first_temp, t.wm1, out_id, T);
+__device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, double seed, const SweepTarget& T, PendingParam& pend) {
+    int rows = sweep_seed<MODE>(t.next_id - t.first_temp, t.first_temp, t.wm1, out_id, seed, T);
     if (rows <= 0) return;
     /* pad to whole batches: the rows above `rows` are dead or were never written */
     const int nb = (rows + 3) >> 2;
@@ -637,13 +766,16 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, co
     for (int j = 0; j < 3; j++) {
         if (rows + j < 4 * nb) *reinterpret_cast<int2*> (t.hdr + (size_t) (rows + j) * kHdrBytes) = make_int2(kNopFlag, 0);
     }
-    UniformSweep<MODE> S{t.hdr, t.cells, t.far_adj, T, t.wm1, 0.0, 0.0};
+    /* (W - 1) << 3, pinned in a register (the compiler otherwise re-derives it from the launch
+       parameters in the constant bank at every use) */
+    unsigned wmask8 = (unsigned) t.wm1 << 3;
+    asm volatile("" : "+r"(wmask8));
+    UniformSweep<MODE> S{t.hdr, t.cells, t.far_adj, T, wmask8, 0.0, pend};
 
     int b = nb - 1;
-    /* shared address of the ring entry of row 4b (W >= 4 and batches are aligned: the four pops of a
-       batch are at +0, +8, +16, +24 from it); stepped down with the batch index, kept in a register */
-    const unsigned ring_span = (unsigned) (t.wm1 + 1) << 3;
-    unsigned rb = (unsigned) ((4 * b) & t.wm1) << 3;
+    /* shared-memory offset of the ring entry of row 4b (W >= 4 and batches are aligned: the four pops of
+       a batch are at +0, +8, +16, +24 from it); stepped down with the batch index */
+    unsigned rb = ((unsigned) (4 * b) << 3) & wmask8;
     unsigned offA[4], offB[4];
     int wordA[4], wordB[4];
     double dxA[4], dxB[4];
@@ -657,71 +789,73 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, co
         S.load_words(b - 1, wordB);
         S.load_offsets(b - 2, offA);
         S.batch(b, T.ring + rb, wordA, dxA);
-        rb = (rb - 32u) & (ring_span - 1u);
+        rb = (rb - 32u) & wmask8;
         if (--b < 0) break;
         /* B holds batch b; A becomes batch b-1 */
         S.load_cells(offA, dxA);
         S.load_words(b - 1, wordA);
         S.load_offsets(b - 2, offB);
         S.batch(b, T.ring + rb, wordB, dxB);
-        rb = (rb - 32u) & (ring_span - 1u);
+        rb = (rb - 32u) & wmask8;
         if (--b < 0) break;
     }
 }
 
 /*
  * General sweep: every lane walks its OWN rows (lanes of a diverged warp hold tapes of different
- * lengths; rows whose id words differ between lanes keep them in the lane-word plane).  Out of
- * line and by value: it runs once per work-item of the (rare) warps that need it, and the hot
- * entry stays small.  Four rows per batch; the headers of the next batch are requested before the
- * cells of the current one are used.  Returns Status bits (AD4CL_DEBUG_BOUNDS builds).
+ * lengths, id words may differ between lanes).  Out of line and by value: the hot entry stays small.
+ * Four rows per batch, fetched one batch ahead of their use.  All lanes of the warp iterate together
+ * (the independents' contributions are reduced with warp votes).  Returns Status bits
+ * (AD4CL_DEBUG_BOUNDS builds).
  */
 template <int MODE>
-static __device__ __noinline__ int tape_sweep_general(const char* hdr, const char* cells, const char* lane_words,
-        char* far_adj, int rows, int first_temp, int wmask, int out_id, SweepTarget T, int cap_rows) {
+static __device__ __noinline__ int tape_sweep_general(const char* cells, const char* lane_words,
+        char* far_adj, int rows, int first_temp, int wmask, int out_id, double seed, SweepTarget T, int cap_rows) {
     constexpr int U = kSweepUnroll;
-    rows = sweep_seed<MODE>(rows, first_temp, wmask, out_id, T);
+    rows = sweep_seed<MODE>(rows, first_temp, wmask, out_id, seed, T);
     int status = kOk;
-    double w = 0.0, carry = 0.0;
-    int2 h_now[U], h_next[U];
+#if AD4CL_DEBUG_BOUNDS
+    if (rows < 0 || rows > cap_rows) {
+        status |= kErrBounds;
+        rows = 0;
+    }
+#endif
+    const unsigned pad_off = (unsigned) (wmask + 1) << 3;
+    double w = 0.0;
+    double dx_now[U], dx_next[U];
+    int id_now[U], id_next[U];
     /* the first batch takes the rows that do not fill a whole batch */
     const int head = rows & (U - 1);
-    int top = rows;                 /* slot j of the current batch has index top - 1 - j */
 #pragma unroll
     for (int j = 0; j < U; j++) {
-        h_now[j] = j < head ? *reinterpret_cast<const int2*> (hdr + (size_t) (top - 1 - j) * kHdrBytes)
-                            : make_int2(kNopFlag, 0);
+        if (j < head) {
+            const int r = rows - 1 - j;
+            dx_now[j] = *reinterpret_cast<const double*> (cells + (size_t) (r + kUnitCells) * kCellRowBytes);
+            id_now[j] = *reinterpret_cast<const int*> (lane_words + (size_t) r * kLaneWordRowBytes);
+        } else {
+            dx_now[j] = 0.0;
+            id_now[j] = kNopFlag;
+        }
     }
+    int top = rows;                 /* slot j of the current batch has index top - 1 - j */
     int next_top = rows - head;
     bool more = true;
     while (__any_sync(0xffffffffu, more)) {
         const bool fetch = next_top > 0;
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            h_next[j] = fetch ? *reinterpret_cast<const int2*> (hdr + (size_t) (next_top - 1 - j) * kHdrBytes)
-                              : make_int2(kNopFlag, 0);
-        }
-        double dx[U];
-        int word[U];
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const unsigned aux = (unsigned) h_now[j].y;
-            const int me = top - 1 - j;
-#if AD4CL_DEBUG_BOUNDS
-            if ((aux & kAuxOffsetMask) > (unsigned) (cap_rows + kUnitCells - 1) * kCellRowBytes || me >= cap_rows) {
-                status |= kErrBounds; /* report and neutralise the row; every lane keeps reaching the votes below */
-                dx[j] = 0.0;
-                word[j] = kNopFlag;
-                continue;
+            if (fetch) {
+                const int r = next_top - 1 - j;
+                dx_next[j] = *reinterpret_cast<const double*> (cells + (size_t) (r + kUnitCells) * kCellRowBytes);
+                id_next[j] = *reinterpret_cast<const int*> (lane_words + (size_t) r * kLaneWordRowBytes);
+            } else {
+                dx_next[j] = 0.0;
+                id_next[j] = kNopFlag;
             }
-#endif
-            dx[j] = *reinterpret_cast<const double*> (cells + (aux & kAuxOffsetMask));
-            word[j] = (aux & kAuxNonUniform) ? *reinterpret_cast<const int*> (lane_words + (size_t) me * kLaneWordRowBytes)
-                                             : h_now[j].x;
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            int idw = word[j];
+            int idw = id_now[j];
             const int me = top - 1 - j;
 #if AD4CL_DEBUG_BOUNDS
             {   /* operands precede their use; independents are below first_temp; far rows need the plane */
@@ -734,41 +868,39 @@ static __device__ __noinline__ int tape_sweep_general(const char* hdr, const cha
                 }
             }
 #endif
-            if (idw < 0) { /* END */
+            if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
                 const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
-                w = lds_f64(r) + carry;
+                w = lds_f64(r);
                 sts_f64(r, 0.0);
-                carry = 0.0;
             }
             if (idw & (kFarFlag | kHasFarFlag)) { /* rare: ONE test for both far cases */
-                if ((idw & kHasFarFlag) && idw < 0) {
+                if ((idw & kHasFarFlag) && idw < 0) { /* contributions that came through the far plane */
                     double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
-                    w += *fa;
+                    w = __dadd_rn(w, *fa);
                     *fa = 0.0;
                 }
                 if ((idw & kFarFlag) && !(idw & kNopFlag) && far_adj != nullptr) {
-                    *reinterpret_cast<double*> (far_adj + (size_t) (idw & kIdMask) * kFarRowBytes) += w * dx[j];
+                    double* fa = reinterpret_cast<double*> (far_adj + (size_t) (idw & kIdMask) * kFarRowBytes);
+                    *fa = __dadd_rn(*fa, __dmul_rn(w, dx_now[j]));
                 }
             }
             const int payload = idw & kIdMask;
-            const double c = w * dx[j];
-            const int cls = idw & (kNopFlag | kParamFlag | kFarFlag | kChainFlag);
-            if (cls == kChainFlag) carry += c;
-            if (cls == 0) {
-                const unsigned a = T.ring + ((unsigned) (payload & wmask) << 3);
-                sts_f64(a, lds_f64(a) + c);
+            const double c = __dmul_rn(w, dx_now[j]);
+            const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
+            {   /* Branch-free scatter: a recent temporary adds to its ring entry, with per-thread
+                   accumulators (kAccThread) an independent adds to its accumulator, and a slot of any
+                   other class adds to the pad entry of this thread's ring (index W), which nothing reads. */
+                unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
+                if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
+                sts_f64(a, __dadd_rn(lds_f64(a), c));
             }
-            if (MODE == kAccThread) {
-                if (cls == kParamFlag) {
-                    const unsigned a = T.thread_acc + (unsigned) payload * T.stride;
-                    sts_f64(a, lds_f64(a) + c);
-                }
-            } else {
-                sweep_param<MODE>(T, cls == kParamFlag, payload, c);
-            }
+            if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
         }
 #pragma unroll
-        for (int j = 0; j < U; j++) h_now[j] = h_next[j];
+        for (int j = 0; j < U; j++) {
+            dx_now[j] = dx_next[j];
+            id_now[j] = id_next[j];
+        }
         top = next_top;
         next_top -= U;
         more = fetch;

@@ -14,8 +14,8 @@
 
 #include "../kernels/objectives.cl"
 
-#define SROW(NAME, SIG, FROZEN_ARG, FROZEN_VALUE) \
-    {#NAME, (const void*) &AD4CL_STATIC_ENTRY_NAME(NAME), SIG, AD4CL_P, FROZEN_ARG, FROZEN_VALUE}
+#define SROW(NAME, SIG, FROZEN_ARG, FROZEN_VALUE, SLOTS) \
+    {#NAME, (const void*) &AD4CL_STATIC_ENTRY_NAME(NAME), SIG, AD4CL_P, FROZEN_ARG, FROZEN_VALUE, SLOTS}
 
 #if AD4CL_P == 2
 AD4CL_STATIC_ENTRY(linreg2_g,
@@ -25,9 +25,9 @@ AD4CL_STATIC_ENTRY(linreg2_p,
     (const struct ad_variable* a, const struct ad_variable* b, double* x, double* y, int size),
     (gs, gradient_stack, th + 0, th + 1, x, y, out, size))
 extern "C" const ad4cl_static_row AD4CL_STATIC_TABLE[] = {
-    SROW(linreg2_g, "GSVVDDOi", -1, 0),
-    SROW(linreg2_p, "GSVVDDOi", -1, 0),
-    {nullptr, nullptr, nullptr, 0, -1, 0},
+    SROW(linreg2_g, "GSVVDDOi", -1, 0, 6),
+    SROW(linreg2_p, "GSVVDDOi", -1, 0, 6),
+    {nullptr, nullptr, nullptr, 0, -1, 0, 0},
 };
 #elif AD4CL_P == 10
 /* i0 (argument 7 of "GSVDDOiii") is the number of parameters = the trip count of the kernel's loop */
@@ -38,9 +38,9 @@ AD4CL_STATIC_ENTRY(regression_logistic,
     (struct ad_variable* theta, double* d0, double* d1, int size, int i0, int i1),
     (gs, gradient_stack, th, d0, d1, out, size, AD4CL_P, i1))
 extern "C" const ad4cl_static_row AD4CL_STATIC_TABLE[] = {
-    SROW(regression_linear, "GSVDDOiii", 7, AD4CL_P),
-    SROW(regression_logistic, "GSVDDOiii", 7, AD4CL_P),
-    {nullptr, nullptr, nullptr, 0, -1, 0},
+    SROW(regression_linear, "GSVDDOiii", 7, AD4CL_P, 3 * AD4CL_P + 1),
+    SROW(regression_logistic, "GSVDDOiii", 7, AD4CL_P, 3 * AD4CL_P + 4),
+    {nullptr, nullptr, nullptr, 0, -1, 0, 0},
 };
 #else
 #error "no register-tier instances for this AD4CL_P"

@@ -28,6 +28,11 @@
 
 extern "C" const ad4cl_builtin_row ad4cl_builtin_table_fixed[];
 extern "C" const ad4cl_builtin_row ad4cl_builtin_table_quirks[];
+/* register-tier instances (builtin_static.cu), one table per (number of independents, quirks) */
+extern "C" const ad4cl_static_row ad4cl_static_table_fixed_p2[];
+extern "C" const ad4cl_static_row ad4cl_static_table_quirks_p2[];
+extern "C" const ad4cl_static_row ad4cl_static_table_fixed_p10[];
+extern "C" const ad4cl_static_row ad4cl_static_table_quirks_p10[];
 extern "C" const char* const ad4cl_embedded_header_names[];
 extern "C" const char* const ad4cl_embedded_header_texts[];
 extern "C" const int ad4cl_embedded_header_count;
@@ -172,6 +177,8 @@ struct ad4cl_kernel {
     std::string name, signature;
     const void* entries[3] = {nullptr, nullptr, nullptr};  /* ahead-of-time kernel, per accumulator mode */
     const void* entry = nullptr;   /* the one selected by prepare() */
+    std::vector<const ad4cl_static_row*> static_rows; /* register-tier instances of this built-in kernel */
+    bool use_static = false;       /* prepare() selected one of them */
     CUmodule module = nullptr;     /* NVRTC kernel */
     CUfunction functions[3] = {nullptr, nullptr, nullptr};
     CUfunction function = nullptr;
@@ -185,6 +192,8 @@ struct ad4cl_kernel {
     int block = 0, grid = 0;
     size_t smem = 0, arena_bytes = 0;
     int launches_per_eval = 1;
+    const double* seeds_dev = nullptr;   /* set around one enqueue by ad4cl_cuda_eval_general */
+    double* out_values_dev = nullptr;
     ad4cl::LaunchInfo L{};
     long long data_items = 0;
     struct ad_variable* params_dev = nullptr;
@@ -261,13 +270,14 @@ ad4cl_kernel* new_kernel(ad4cl_context* ctx, const char* name, const char* sig) 
 }
 
 int occupancy(ad4cl_kernel* k, int block, size_t smem, int* blocks) {
+    /* the entry's static shared memory (~3 KB) counts against the 48 KB default as well: opt in early */
     if (!k->module) {
-        if (smem > 48 * 1024)
+        if (smem > 40 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(k->entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k->entry, block, smem));
     } else {
         DriverApi& d = driver();
-        if (smem > 48 * 1024) {
+        if (smem > 40 * 1024) {
             CUresult r = d.cuFuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) smem);
             if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed: %d", smem, (int) r);
         }
@@ -313,11 +323,53 @@ int prepare(ad4cl_kernel* k, int nparams) {
     int window = c.window > 0 ? pow2_at_least(c.window) : (far ? 16 : pow2_at_least((int) cap_slots + 1));
     window = std::max(window, 4); /* the uniform sweep pops a batch of 4 consecutive ring entries */
     int tier = c.tape_tier;
-    if (tier == AD4CL_TAPE_AUTO) tier = AD4CL_TAPE_HBM;
-    const bool fused = acc != AD4CL_ACC_GLOBAL && nparams <= ad4cl::kInKernelPackMax;
+    /* Tier choice.  REGISTER (ad4cl_tape.cuh, AD4CL_TAPE_STATIC): the kernel has an instance compiled for
+       exactly this many independents, bound as params(0..P) in argument order, and for the value of the
+       integer argument that instance froze; AUTO additionally requires that the instance really was
+       scalarised (no local memory).  Otherwise AUTO = the HBM arena, which stays L2 resident for short
+       tapes; the shared-memory tier is only ever chosen explicitly. */
+    const ad4cl_static_row* srow = nullptr;
+    if (tier == AD4CL_TAPE_AUTO || tier == AD4CL_TAPE_REGISTER) {
+        for (const ad4cl_static_row* r : k->static_rows) {
+            if (r->nparams != nparams) continue;
+            bool ok = (unsigned) r->slots <= cap_slots;   /* a deliberately short tape keeps its overflow report */
+            if (g1 != 1) ok = false;                      /* the instances are 1-D kernels */
+            /* AUTO leaves explicit choices of the arena machinery alone */
+            if (tier == AD4CL_TAPE_AUTO && (c.window != 0 || c.far_plane == 0
+                    || (c.acc_mode != AD4CL_ACC_AUTO && c.acc_mode != AD4CL_ACC_THREAD))) ok = false;
+            int next = 0;
+            for (const Arg& a : k->args) {
+                if (a.kind != 'V') continue;
+                if (a.first_id != next) ok = false;
+                next += a.count;
+            }
+            if (next != nparams) ok = false;
+            if (ok && r->frozen_arg >= 0 && (r->frozen_arg >= (int) k->args.size() || !k->args[r->frozen_arg].set
+                    || k->args[r->frozen_arg].ival != r->frozen_value)) ok = false;
+            if (ok && tier == AD4CL_TAPE_AUTO) {
+                cudaFuncAttributes fa{};
+                if (cudaFuncGetAttributes(&fa, r->entry) != cudaSuccess || fa.localSizeBytes != 0) ok = false;
+                cudaGetLastError();
+            }
+            if (ok) {
+                srow = r;
+                break;
+            }
+        }
+        if (tier == AD4CL_TAPE_REGISTER && !srow)
+            return fail(AD4CL_ERR_INVALID, "kernel %s has no register-tier instance for %d independents with these "
+                    "arguments (built-in instances: linreg2_g / linreg2_p with 2, regression_* with 10)", k->name.c_str(), nparams);
+        tier = srow ? AD4CL_TAPE_REGISTER : AD4CL_TAPE_HBM;
+    }
+    k->use_static = srow != nullptr;
+    if (srow) {
+        acc = AD4CL_ACC_THREAD; /* per-thread REGISTER accumulators */
+        k->entry = srow->entry;
+    }
+    const bool fused = srow != nullptr || (acc != AD4CL_ACC_GLOBAL && nparams <= ad4cl::kInKernelPackMax);
 
-    const size_t smem = ad4cl::entry_smem_bytes(block, nparams, window, acc, tier == AD4CL_TAPE_SHARED,
-            cap_slots, far);
+    const size_t smem = srow ? sizeof (double) * (size_t) (block / 32) * (nparams + 3)
+            : ad4cl::entry_smem_bytes(block, nparams, window, acc, tier == AD4CL_TAPE_SHARED, cap_slots, far);
     if (smem > k->ctx->prop.sharedMemPerBlockOptin)
         return fail(AD4CL_ERR_INVALID, "kernel %s needs %zu B of shared memory per block (limit %zu): "
                 "lower window/local size or use AD4CL_ACC_WARP", k->name.c_str(), smem,
@@ -332,7 +384,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     grid = std::max(grid, 1);
 
     const size_t region = ad4cl::warp_region_bytes(cap_slots, far);
-    const size_t arena_bytes = tier == AD4CL_TAPE_SHARED ? 0 : (size_t) grid * (block / 32) * region;
+    const size_t arena_bytes = tier != AD4CL_TAPE_HBM ? 0 : (size_t) grid * (block / 32) * region;
     const int ncols = nparams + 3;
     const int pcols = (acc == AD4CL_ACC_GLOBAL ? 0 : nparams) + 3; /* columns of the per-block partials */
 
@@ -364,6 +416,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.n_items = g0 * g1;
     L.g0 = (int) g0;
     L.g0_user = (int) c.global_size[0];
+    L.n_user = c.global_size[0] * (c.global_size[1] > 0 ? c.global_size[1] : 1);
     L.l0 = l0;
     L.nparams = nparams;
     L.recording = 1;
@@ -391,6 +444,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     k->stats.block = block;
     k->stats.smem_bytes = smem;
     k->stats.arena_bytes = arena_bytes;
+    k->stats.tape_tier = tier;
     k->ready = true;
     return AD4CL_OK;
 }
@@ -420,7 +474,7 @@ int drain_profile(ad4cl_kernel* k) {
  * independents) the parameters are packed and the partial rows reduced by separate small launches.
  */
 int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue,
-        double* status_out = nullptr, ad4cl_comm* comm = nullptr);
+        double* status_out = nullptr, ad4cl_comm* comm = nullptr, const int* skip_dev = nullptr);
 
 int status_to_error(ad4cl_kernel* k, int st);
 
@@ -440,7 +494,7 @@ struct ad4cl_comm {
 namespace {
 
 int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int want_gradient, int apply_epilogue,
-        double* status_out, ad4cl_comm* comm) {
+        double* status_out, ad4cl_comm* comm, const int* skip_dev) {
     cudaStream_t st = k->ctx->stream;
     const int P = k->nparams;
     if (comm != nullptr && comm->world > 1 && !k->fused)
@@ -448,6 +502,9 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
                 "(accumulator mode thread or warp, at most %d independents)", k->name.c_str(), ad4cl::kInKernelPackMax);
     ad4cl::LaunchInfo L = k->L;
     L.recording = want_gradient ? 1 : 0;
+    L.skip = skip_dev;
+    L.seeds = k->seeds_dev;
+    L.out_values = k->out_values_dev;
     const double n_obs = k->cfg.epilogue_n > 0 ? k->cfg.epilogue_n : (double) k->data_items;
     const int epi = apply_epilogue ? k->cfg.epilogue : 0;
     if (k->fused) {
@@ -699,6 +756,11 @@ int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int referenc
         if (strcmp(r->name, name) == 0) {
             ad4cl_kernel* k = new_kernel(ctx, name, r->signature);
             for (int m = 0; m < 3; m++) k->entries[m] = r->entry[m];
+            const ad4cl_static_row* const stabs[2][2] = {{ad4cl_static_table_fixed_p2, ad4cl_static_table_fixed_p10},
+                {ad4cl_static_table_quirks_p2, ad4cl_static_table_quirks_p10}};
+            for (const ad4cl_static_row* st : stabs[reference_quirks ? 1 : 0])
+                for (; st->name; st++)
+                    if (strcmp(st->name, name) == 0) k->static_rows.push_back(st);
             k->cfg.reference_quirks = reference_quirks;
             *out = k;
             return AD4CL_OK;
@@ -743,6 +805,11 @@ static int compile_to_cubin(const char* source, const char* entry, const char* s
     if (rc != 0) return fail(AD4CL_ERR_COMPILE, "nvrtcCreateProgram failed: %d", rc);
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
         std::string("-DAD4CL_REFERENCE_QUIRKS=") + (reference_quirks ? "1" : "0")};
+    /* a kernel that synchronises its work-group cannot be re-run by a single warp after a failed optimistic
+       recording attempt (ad4cl_entry.cuh): build it with the general recorder only */
+    if (strstr(source, "barrier") != nullptr || strstr(source, "__syncthreads") != nullptr || strstr(source, "__local") != nullptr
+            || strstr(source, "__shared__") != nullptr)
+        opts.push_back("-DAD4CL_BODY_HAS_BARRIER=1");
     if (options) {
         std::string o(options);
         size_t pos = 0;
@@ -927,6 +994,20 @@ int ad4cl_cuda_eval_device(ad4cl_kernel* k, const double* theta_dev, int nparams
     return enqueue(k, theta_dev, result_dev, want_gradient, apply_epilogue);
 }
 
+int ad4cl_cuda_eval_device_if(ad4cl_kernel* k, const double* theta_dev, int nparams, double* result_dev,
+        int want_gradient, int apply_epilogue, const int* skip_dev) {
+    if (!k || !result_dev || (!theta_dev && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    int rc = prepare(k, nparams);
+    if (rc != AD4CL_OK) return rc;
+    if (skip_dev != nullptr && !k->fused)
+        return fail(AD4CL_ERR_INVALID, "kernel %s: a predicated evaluation needs the single-launch path "
+                "(accumulator mode thread or warp)", k->name.c_str());
+    return enqueue(k, theta_dev, result_dev, want_gradient, apply_epilogue, nullptr, nullptr, skip_dev);
+}
+
+ad4cl_context* ad4cl_cuda_kernel_context(ad4cl_kernel* k) { return k ? k->ctx : nullptr; }
+
 int ad4cl_cuda_eval_device_sharded(ad4cl_kernel* k, ad4cl_comm* comm, const double* theta_dev, int nparams,
         double* result_dev, int want_gradient) {
     if (!k || !comm || !result_dev || (!theta_dev && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
@@ -1037,6 +1118,37 @@ int ad4cl_cuda_eval_sharded(ad4cl_kernel* k, ad4cl_comm* comm, const double* the
 }
 
 int ad4cl_cuda_launches_per_eval(ad4cl_kernel* k) { return k ? k->launches_per_eval : 0; }
+
+int ad4cl_cuda_eval_general(ad4cl_kernel* k, const double* theta, int nparams, double* out_values_dev,
+        const double* seeds_dev, double* sum, double* grad) {
+    if (!k || (!theta && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(k->ctx->device));
+    int rc = prepare(k, nparams);
+    if (rc != AD4CL_OK) return rc;
+    cudaStream_t st = k->ctx->stream;
+    if (nparams > 0) {
+        memcpy(k->theta_pinned, theta, sizeof (double) * (size_t) nparams);
+        CUDA_TRY(cudaMemcpyAsync(k->theta_dev, k->theta_pinned, sizeof (double) * (size_t) nparams, cudaMemcpyHostToDevice, st));
+    }
+    k->seeds_dev = seeds_dev;
+    k->out_values_dev = out_values_dev;
+    rc = enqueue(k, k->theta_dev, k->result_dev, grad != nullptr ? 1 : 0, 0, k->result_dev + nparams + 3);
+    k->seeds_dev = nullptr;
+    k->out_values_dev = nullptr;
+    if (rc != AD4CL_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(k->result_pinned, k->result_dev, sizeof (double) * (size_t) (nparams + 4), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!k->fused) { /* the separate second stage writes the status only on the fused path */
+        rc = ad4cl_cuda_check(k);
+        if (rc != AD4CL_OK) return rc;
+    } else {
+        rc = status_to_error(k, (int) k->result_pinned[nparams + 3]);
+        if (rc != AD4CL_OK) return rc;
+    }
+    if (sum) *sum = k->result_pinned[nparams];
+    if (grad) memcpy(grad, k->result_pinned, sizeof (double) * (size_t) nparams);
+    return AD4CL_OK;
+}
 
 int ad4cl_cuda_kernel_profile(ad4cl_kernel* k, int enable) {
     if (!k) return fail(AD4CL_ERR_INVALID, "kernel is NULL");
@@ -1211,6 +1323,22 @@ int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, in
     static_assert(sizeof (HostEntry) == 40 && sizeof (HostVar) == 16, "reference layouts (ad.cl:65-79)");
     if (!k || !entries_out || !n_entries || (!theta && nparams > 0)) return fail(AD4CL_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(k->ctx->device));
+    /* the export reads tape rows out of the arena: a kernel that would run in the register or the
+       shared-memory tier is prepared for the arena tier for this call */
+    struct TierGuard {
+        ad4cl_kernel* k;
+        int saved;
+        ~TierGuard() {
+            if (k->cfg.tape_tier != saved) {
+                k->cfg.tape_tier = saved;
+                k->ready = false;
+            }
+        }
+    } guard{k, k->cfg.tape_tier};
+    if (k->cfg.tape_tier != AD4CL_TAPE_HBM) {
+        k->cfg.tape_tier = AD4CL_TAPE_HBM;
+        k->ready = false;
+    }
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
     cudaStream_t st = k->ctx->stream;
@@ -1285,15 +1413,12 @@ int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, in
         HostEntry cur{};
         int have = 0;
         for (int s = 0; s < nslots; s++) {
-            /* header {id word, cell offset | flags}; a non-uniform row keeps its id word per lane */
-            int hdr[2];
-            memcpy(hdr, col + (size_t) s * ad4cl::kHdrBytes, 8);
-            const unsigned aux = (unsigned) hdr[1];
-            int word = hdr[0];
-            if (aux & ad4cl::kAuxNonUniform)
-                memcpy(&word, col + lay.off_lane_words + (size_t) s * ad4cl::kLaneWordRowBytes + lane * 4, 4);
+            /* the export launch records with the general recorder: row s = this lane's id word in the
+               lane-word plane and its partial in cell s + 2 (ad4cl_tape.cuh) */
+            int word;
+            memcpy(&word, col + lay.off_lane_words + (size_t) s * ad4cl::kLaneWordRowBytes + lane * 4, 4);
             double dx;
-            memcpy(&dx, col + lay.off_cells + (aux & ad4cl::kAuxOffsetMask) + lane * 8, 8);
+            memcpy(&dx, col + lay.off_cells + (size_t) (s + ad4cl::kUnitCells) * ad4cl::kCellRowBytes + lane * 8, 8);
             if (!(word & ad4cl::kNopFlag)) {
                 const int payload = word & ad4cl::kIdMask;
                 const int id = (word & ad4cl::kParamFlag) ? payload : base + op_of_slot[(size_t) payload];

@@ -25,7 +25,7 @@ LIB_PATH = os.environ.get("AD4CL_CUDA_LIB", os.path.join(_HERE, "libad4cl_cuda.s
 
 OK, ERR_CUDA, ERR_INVALID, ERR_TAPE_OVERFLOW, ERR_WINDOW, ERR_COMPILE, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 ACC = {"auto": -1, "thread": 0, "warp": 1, "global": 2}
-TAPE = {"auto": -1, "hbm": 0, "shared": 1}
+TAPE = {"auto": -1, "hbm": 0, "shared": 1, "register": 2}
 PREFETCH = {"auto": -1, "off": 0, "on": 1}
 EPILOGUE = {"sum": 0, "half_n_log": 1}
 
@@ -56,7 +56,7 @@ class LbfgsResult(ctypes.Structure):
 class EvalStats(ctypes.Structure):
     _fields_ = [("ops", c_double), ("slots", c_double), ("grid", c_int), ("block", c_int),
                 ("smem_bytes", c_size_t), ("arena_bytes", c_size_t), ("kernel_ms", c_float),
-                ("sweep_prefetch", c_int)]
+                ("sweep_prefetch", c_int), ("tape_tier", c_int)]
 
 
 def _load() -> ctypes.CDLL:
@@ -120,6 +120,11 @@ def _load() -> ctypes.CDLL:
     lib.ad4cl_cuda_eval_sharded.argtypes = [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), c_void_p]
     lib.ad4cl_cuda_eval_device_sharded.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]
     lib.ad4cl_cuda_launches_per_eval.argtypes = [c_void_p]
+    if hasattr(lib, "ad4cl_cuda_eval_general"):
+        lib.ad4cl_cuda_eval_general.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_double), c_void_p]
+    if hasattr(lib, "ad4cl_cuda_minimize_lbfgs_device"):
+        lib.ad4cl_cuda_minimize_lbfgs_device.argtypes = [c_void_p, c_void_p, c_int, POINTER(LbfgsOptions), POINTER(LbfgsResult)]
+        lib.ad4cl_cuda_eval_device_if.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
     return lib
 
 
@@ -271,6 +276,22 @@ class Kernel:
         _check(lib.ad4cl_cuda_eval_device_sharded(self._h, comm._h, theta_dev_ptr, nparams, result_dev_ptr,
                                                   1 if want_grad else 0))
 
+    def eval_outputs(self, theta, n: int):
+        """Pass 1 of a general epilogue: -> (sum_i out_i, Buffer holding out_i.value for the n work-items)."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        out = self.ctx.buffer(nbytes=8 * n)
+        s = c_double()
+        _check(lib.ad4cl_cuda_eval_general(self._h, th.ctypes.data, len(th), out.device_ptr, None, byref(s), None))
+        return s.value, out
+
+    def eval_seeded(self, theta, seeds: "Buffer"):
+        """Pass 2: the gradient of sum_i seeds_i * out_i(theta) (seeds: device Buffer of n doubles) -> grad[P]."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        g = np.empty(len(th))
+        s = c_double()
+        _check(lib.ad4cl_cuda_eval_general(self._h, th.ctypes.data, len(th), None, seeds.device_ptr, byref(s), g.ctypes.data))
+        return g
+
     @property
     def launches_per_eval(self) -> int:
         """Kernel launches of the last evaluation enqueued (1 unless acc = global)."""
@@ -294,21 +315,25 @@ class Kernel:
                                           byref(n), out.ctypes.data, n_out))
         return entries[: n.value], out
 
-    def minimize(self, theta0, **options):
-        """L-BFGS inside the library (ad4cl_cuda_minimize_lbfgs) -> (theta, dict of the result fields)."""
+    def minimize(self, theta0, device_resident: bool = True, **options):
+        """L-BFGS inside the library -> (theta, dict of the result fields).  device_resident (default): the
+        whole fit runs on the GPU as CUDA graphs of (evaluation, lbfgs_update) pairs, no host round trip
+        between evaluations (ad4cl_cuda_minimize_lbfgs_device); False: the host loop over ad4cl_cuda_eval."""
         th = np.array(theta0, dtype=np.float64, copy=True)
         opt, res = LbfgsOptions(), LbfgsResult()
         _check(lib.ad4cl_cuda_lbfgs_options_default(byref(opt)))
         for key, v in options.items():
             setattr(opt, key, v)
-        _check(lib.ad4cl_cuda_minimize_lbfgs(self._h, th.ctypes.data, len(th), byref(opt), byref(res)))
+        fn = lib.ad4cl_cuda_minimize_lbfgs_device if device_resident else lib.ad4cl_cuda_minimize_lbfgs
+        _check(fn(self._h, th.ctypes.data, len(th), byref(opt), byref(res)))
         return th, {name: getattr(res, name) for name, _ in LbfgsResult._fields_}
 
     def stats(self) -> dict:
         s = EvalStats()
         _check(lib.ad4cl_cuda_last_stats(self._h, byref(s)))
         return {"ops": s.ops, "slots": s.slots, "grid": s.grid, "block": s.block, "smem_bytes": s.smem_bytes,
-                "arena_bytes": s.arena_bytes, "kernel_ms": s.kernel_ms, "sweep_prefetch": s.sweep_prefetch}
+                "arena_bytes": s.arena_bytes, "kernel_ms": s.kernel_ms, "sweep_prefetch": s.sweep_prefetch,
+                "tape_tier": {v: k for k, v in TAPE.items()}.get(s.tape_tier, str(s.tape_tier))}
 
     def profile(self, enable: bool = True) -> None:
         """CUDA-event timing of the fused kernel alone (CL_PROFILING analogue)."""

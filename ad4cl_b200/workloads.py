@@ -29,6 +29,7 @@ class Workload:
     max_slots: int = 0
     ops_total: int = 0        # per evaluation, for the roofline arithmetic
     slots_total: int = 0
+    cells_total: int = 0      # operand slots whose partial is not a compile-time +1 / -1 (they own a tape cell)
     input_bytes: int = 0      # data bytes read once per evaluation
     linreg2: bool = False     # (a, b) passed as two separate V arguments (simple.cl signature)
     matrix: int = 0           # n of an n x n matrix kernel (A, B as 2 n^2 independents, 2-D NDRange)
@@ -42,6 +43,13 @@ class Workload:
         """24 B per operand slot (12 written forward + 12 read in
         reverse) + inputs read once + 8 (P+1) out."""
         return 24 * self.slots_total + self.input_bytes + 8 * (self.nparams + 1)
+
+    def minimal_record_bytes(self) -> int:
+        """What the round-2 tape stream moves when a work-item is warp-uniform (ad4cl_tape.cuh): an 8-byte
+        header per WARP row (0.25 B per lane and slot) and an 8-byte cell per lane only for non-unit
+        partials, each written once and read once, + inputs + 8 (P+1) out."""
+        cells = self.cells_total if self.cells_total else self.slots_total
+        return 2 * (8 * cells + self.slots_total // 4) + self.input_bytes + 8 * (self.nparams + 1)
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
@@ -61,17 +69,18 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
                             epilogue_n=n, max_ops=4, max_slots=6, ops_total=2 * count, slots_total=3 * count,
                             input_bytes=16 * count, linreg2=True)
         return Workload(name, "linreg2_p", np.array([a, b]), x, y, count, epilogue="half_n_log", epilogue_n=n,
-                        max_ops=4, max_slots=6, ops_total=4 * count, slots_total=6 * count,
+                        max_ops=4, max_slots=6, ops_total=4 * count, slots_total=6 * count, cells_total=3 * count,
                         input_bytes=16 * count, linreg2=True)
     if name in ("regression_linear", "regression_logistic"):
         kind = name.split("_")[1]
         X, y, beta = synth.regression(n, p, kind, start, count)
         ops = (2 * p + 1) if kind == "linear" else (2 * p + 4)
         slots = (3 * p + 1) if kind == "linear" else (3 * p + 4)
+        cells = (p + 2) if kind == "linear" else (p + 3)      # the rest are +1 / -1 partials of plus / minus
         return Workload(name, name, beta, X, y, count, i0=p,
                         epilogue="half_n_log" if kind == "linear" else "sum", epilogue_n=n,
                         max_ops=ops, max_slots=slots, ops_total=ops * count, slots_total=slots * count,
-                        input_bytes=8 * (p + 1) * count)
+                        cells_total=cells * count, input_bytes=8 * (p + 1) * count)
     if name == "catch_at_age":
         # tape length varies 4x with age: every rank takes a slice of the REPLICATES of every
         # (year, age) cell, so all shards have the same mix (a contiguous observation range would not)
@@ -79,15 +88,16 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
         rep0, nrep = shard_range(R, rank, world)
         obs, theta0, _ = synth.catch_at_age(n, rep0, nrep)
         ops, slots = caa_totals(nrep)
+        cells = nrep * sum(c for _, _, c in _caa_per_cell())
         return Workload(name, name, theta0, obs, np.array([float(R)]), len(obs), i0=nrep, i1=rep0, max_ops=128, max_slots=176,
-                        ops_total=ops, slots_total=slots, input_bytes=8 * len(obs))
+                        ops_total=ops, slots_total=slots, cells_total=cells, input_bytes=8 * len(obs))
     if name == "tape_stress":
         x, theta = synth.tape_stress(n, start, count)
         theta = np.ones(p)
         ops, slots = 3 * steps + 1, 4 * steps + 1
         return Workload(name, name, theta, x, None, count, i0=steps, i1=p, max_ops=ops, max_slots=slots,
-                        ops_total=ops * count, slots_total=slots * count, input_bytes=8 * count,
-                        extra={"steps": steps})
+                        ops_total=ops * count, slots_total=slots * count, cells_total=(2 * steps + 1) * count,
+                        input_bytes=8 * count, extra={"steps": steps})
     if name in ("matrix_product", "matrix_elementwise"):
         # config 2: test/matrix (matrix_mul.cpp:84-90 inputs); n is the matrix dimension here
         A, B = synth.msvcrt_rand_matrices(n)
@@ -106,41 +116,51 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
     raise KeyError(name)
 
 
+def tape_stress_with_steps(w: Workload, steps: int) -> Workload:
+    """The same tape_stress shard with another tape length (the data do not depend on it)."""
+    import dataclasses
+    ops, slots = 3 * steps + 1, 4 * steps + 1
+    return dataclasses.replace(w, i0=steps, max_ops=ops, max_slots=slots, ops_total=ops * w.size,
+                               slots_total=slots * w.size, cells_total=(2 * steps + 1) * w.size, extra={"steps": steps})
+
+
 def caa_totals(nrep: int) -> tuple[int, int]:
     """AD operators and operand slots of catch_at_age over `nrep` replicates of every cell."""
     per_cell = _caa_per_cell()
-    return nrep * sum(o for o, _ in per_cell), nrep * sum(sl for _, sl in per_cell)
+    return nrep * sum(o for o, _, _ in per_cell), nrep * sum(sl for _, sl, _ in per_cell)
 
 
 _CAA_CACHE: list | None = None
 
 
 def _caa_per_cell():
-    """(ops, slots) one work-item of cell = year + 40*age records; counted from the
-    kernel text of catch_at_age (objectives.cl) -- checked against the device's own
-    counters in tests/test_gpu_parity.py."""
+    """(ops, slots, cells) one work-item of cell = year + 40*age records; counted from the
+    kernel text of catch_at_age (objectives.cl) -- ops and slots are checked against the device's
+    own counters in tests/test_gpu_parity.py.  cells = slots whose partial is not +1 / -1."""
     global _CAA_CACHE
     if _CAA_CACHE is None:
         out = []
         for age in range(synth.CAA_AGES):
             for year in range(synth.CAA_YEARS):
-                o = s = 1
+                o = s = c = 1
                 have = False
                 for kk in range(age + 1):
                     if year - age + kk >= 0:
                         o += 9
                         s += 12
+                        c += 8          # minus_dv, plus_vd and plus (2 slots) carry unit partials
                     if kk < age:
                         if have:
                             o += 1
-                            s += 2
+                            s += 2      # plus: both unit
                         have = True
                 if have:
                     o += 1
-                    s += 2
+                    s += 2              # minus: both unit
                 o += 18
                 s += 27
-                out.append((o, s))
+                c += 21                 # of the 27: minus_dv, plus (2), minus_dv, plus (2) are unit
+                out.append((o, s, c))
         # cell index = year + 40*age: the loops above ran age-major, year-minor
         _CAA_CACHE = out
     return _CAA_CACHE

@@ -187,6 +187,233 @@ def opencl_reference_rate(workload: str, n_full: int, n_sample: int):
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
+
+# ----------------------------------------------------------------------------- the other BASELINE configs
+def tape_stress_closed_form(sum_x: float, steps: int, P: int):
+    """config 5 has a closed form: v_0 = theta_0 x, v_{j+1} = v_j / 2 + theta_{j mod P} x, objective = sum_i v_steps.
+    With theta = 1: f = sum(x) (2 - 2^-steps); df/dtheta_p = sum(x) * sum of 2^-(steps-1-j) over the steps j that use
+    theta_p (+ 2^-steps for p = 0, from v_0)."""
+    g = np.zeros(P)
+    for j in range(max(0, steps - 1100), steps):        # older terms are below 2^-1100
+        g[j % P] += 2.0 ** -(steps - 1 - j)
+    g[0] += 2.0 ** -steps
+    f = 2.0 - 2.0 ** -steps
+    return sum_x * f, sum_x * g
+
+
+def time_workload(k, P, theta, dev, stream, flush, steps, warmup):
+    """-> (mean fused-kernel ms, mean ms per evaluation incl. everything on the stream, result vector)."""
+    import torch
+    th = torch.from_numpy(np.ascontiguousarray(theta)).to(dev)
+    res = torch.zeros(P + 3, dtype=torch.float64, device=dev)
+    for _ in range(warmup):
+        k.eval_device(th.data_ptr(), P, res.data_ptr())
+    torch.cuda.synchronize(dev)
+    k.check()
+    k.profile(True)
+    k.profile_read(reset=True)
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        e0[i].record(stream)
+        k.eval_device(th.data_ptr(), P, res.data_ptr())
+        e1[i].record(stream)
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / steps
+    kms, _ = k.profile_read(reset=True)
+    k.profile(False)
+    k.check()
+    return kms, ms, res.cpu().numpy()
+
+
+def roofline_row(w, kernel_ms, peak):
+    """The two tape-byte definitions: SURVEY 8(d) (24 B per operand slot: what round 1 stored) and the minimal
+    record of the round-2 stream (8-byte header per WARP row + an 8-byte cell per lane only for non-unit
+    partials, written once and read once); plus the input stream, which is what binds a register-tier kernel."""
+    t = kernel_ms * 1e-3
+    a = w.algorithmic_bytes() / t / 1e9
+    m = w.minimal_record_bytes() / t / 1e9
+    i = w.input_bytes / t / 1e9
+    return {"bound": "hbm", "achieved": a, "frac": a / peak, "minimal_record_GBps": m, "minimal_record_frac": m / peak,
+            "input_stream_GBps": i, "input_stream_frac": i / peak, "unit": "GB/s", "peak": peak}
+
+
+def extra_configs(ctx, dev, stream, flush, peak, with_oracle):
+    """BASELINE configs 1, 2, 3 and 5 (1 GPU, short runs after the headline's timed region): one row each with
+    the fused kernel's time, evaluations/s, roofline fractions and -- when the CPU oracle is available (the
+    baseline leg) -- the relative error of objective and gradient against it on a small instance of the same
+    workload (closed forms for the matrix and tape-stress rows)."""
+    import torch
+    from ad4cl_b200 import synth, workloads as W
+    rows = []
+    orc = None
+    if with_oracle:
+        try:
+            sys.path.insert(0, os.path.join(REPO, "oracle"))
+            import oracle_api as O
+            orc = O.best(False)
+        except Exception:  # noqa: BLE001
+            orc = None
+
+    def rel(x, ref):
+        x, ref = np.atleast_1d(np.asarray(x, dtype=np.float64)), np.atleast_1d(np.asarray(ref, dtype=np.float64))
+        return float(np.max(np.abs(x - ref)) / max(float(np.abs(ref).max()), 1e-300))
+
+    def parity_small(name, n_small, **kw):
+        if orc is None:
+            return None
+        ws = W.describe(name, n_small, **kw)
+        ks = W.bind(ctx, ws)
+        f, g = ks.eval(ws.theta)
+        ks.free()
+        r = orc.eval_objective(ws.kernel, ws.theta, ws.d0, ws.d1, ws.size, ws.i0, ws.i1,
+                               epilogue=1 if ws.epilogue == "half_n_log" else 0, ops_per_item=ws.max_ops)
+        return max(rel(f, r["f"]), rel(g, r["grad"]))
+
+    specs = [("config 1: shipped example (simple.cl), 10^6 observations x 2 parameters", "linreg2_simple", 1_000_000, {}, 20000),
+             ("config 3: linear regression NLL, 10^6 x 10", "regression_linear", 1_000_000, {}, 20000),
+             ("config 3: logistic regression NLL, 10^6 x 10", "regression_logistic", 1_000_000, {}, 20000),
+             ("config 5: tape stress, 10^7 work-items x 100 operators", "tape_stress", 10_000_000, {"steps": 33}, 0),
+             ("config 5: tape stress, 10^7 work-items x 1000 operators", "tape_stress", 10_000_000, {"steps": 333}, 0),
+             ("config 5: tape stress, 2*10^6 work-items x 10^4 operators", "tape_stress", 2_000_000, {"steps": 3333}, 0)]
+    for label, name, n, kw, n_small in specs:
+        try:
+            w = W.describe(name, n, **kw)
+            k = W.bind(ctx, w)
+            kms, ms, res = time_workload(k, w.nparams, w.theta, dev, stream, flush, steps=5, warmup=2)
+            st = k.stats()
+            k.free()
+            row = {"workload": label, "kernel": w.kernel, "n": n, "n_params": w.nparams, "kernel_ms": kms,
+                   "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "tape_tier": st["tape_tier"],
+                   "arena_bytes": st["arena_bytes"], "ad_ops_per_eval": int(res[w.nparams + 1]),
+                   "roofline": roofline_row(w, kms, peak)}
+            if name == "tape_stress":
+                f_ref, g_ref = tape_stress_closed_form(float(np.sum(w.d0)), kw["steps"], w.nparams)
+                row["parity_rel_err"] = max(rel(res[w.nparams], f_ref), rel(res[:w.nparams], g_ref))
+                row["parity_against"] = "closed form at the full size"
+            else:
+                row["parity_rel_err"] = parity_small(name, n_small)
+                row["parity_against"] = f"CPU oracle ({orc.kind}) on {n_small} observations" if orc is not None else None
+            rows.append(row)
+        except Exception as e:  # noqa: BLE001 -- an extra row never fails the headline
+            rows.append({"workload": label, "error": f"{type(e).__name__}: {e}"[:300]})
+        torch.cuda.synchronize(dev)
+
+    # config 2, n = 1024: the tape path (2 n operators per element of C = A B, fp64 atomics into 2 n^2 gradient
+    # cells) and the dense-contraction path (three GEMMs); both against the closed form of d(sum C)
+    try:
+        n = 1024
+        A, B = synth.msvcrt_rand_matrices(n)
+        Am, Bm = A.reshape(n, n), B.reshape(n, n)
+        f_ref = float((Am.sum(axis=0) * Bm.sum(axis=1)).sum())
+        gA = np.repeat(Bm.sum(axis=1)[None, :], n, axis=0).ravel()
+        gB = np.repeat(Am.sum(axis=0)[:, None], n, axis=1).ravel()
+        w = W.describe("matrix_product", n)
+        k = W.bind(ctx, w)
+        kms, ms, res = time_workload(k, w.nparams, w.theta, dev, stream, flush, steps=3, warmup=1)
+        k.free()
+        P2 = w.nparams
+        rows.append({"workload": "config 2: matrix product 1024 x 1024 through the tape", "kernel": "matrix_product", "n": n,
+                     "n_params": P2, "kernel_ms": kms, "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "tape_tier": "hbm",
+                     "ad_ops_per_eval": int(res[P2 + 1]), "roofline": roofline_row(w, kms, peak),
+                     "parity_rel_err": max(rel(res[P2], f_ref), rel(res[:P2], np.concatenate([gA, gB]))),
+                     "parity_against": "closed form d(sum A B) at n = 1024"})
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        A_t, B_t = t(A), t(B)
+        C_t, dA_t, dB_t = (torch.empty(n * n, dtype=torch.float64, device=dev) for _ in range(3))
+        tot = torch.zeros(1, dtype=torch.float64, device=dev)
+        ws = torch.empty(2 * n * n + 4096, dtype=torch.float64, device=dev)
+        wrap = lambda x: ctx.wrap(x.data_ptr(), x.numel() * 8)  # noqa: E731
+        fp64_peak = ctx.measure_fp64_peak()
+        run = lambda: ctx.matrix_product_dense(n, wrap(A_t), wrap(B_t), C=wrap(C_t), dA=wrap(dA_t), dB=wrap(dB_t),  # noqa: E731
+                                               total=wrap(tot), workspace=wrap(ws), variant=1)
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            run()
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        tf = 3 * 2 * n ** 3 / (ms * 1e-3) / 1e12
+        rows.append({"workload": "config 2: matrix product 1024 x 1024, dense contraction (C, sum C, dL/dA, dL/dB)",
+                     "kernel": "dgemm_mma (fp64 tensor core)", "n": n, "kernel_ms": ms, "ms_per_eval": ms, "evals_per_s": 1e3 / ms,
+                     "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                                  "peak_source": "measured fp64 FMA rate of this GPU (ad4cl_cuda_measure_fp64_peak)"},
+                     "parity_rel_err": max(rel(float(tot.item()), f_ref), rel(dA_t.cpu().numpy(), gA), rel(dB_t.cpu().numpy(), gB)),
+                     "parity_against": "closed form d(sum A B) at n = 1024"})
+    except Exception as e:  # noqa: BLE001
+        rows.append({"workload": "config 2: matrix product 1024 x 1024", "error": f"{type(e).__name__}: {e}"[:300]})
+    return rows
+
+
+def config5_sharded(ctx, dev, stream, flush, peak, rank, world, comm, total_items=100_000_000):
+    """BASELINE config 5 at its stated size, 10^8 work-items sharded over the ranks, L = 10^2, 10^3, 10^4 operators:
+    one row per tape length (time of an evaluation = max over ranks, tape GB/s against world x the HBM peak,
+    parity against the closed form).  Collective: every rank takes part."""
+    import torch
+    import torch.distributed as dist
+    from ad4cl_b200 import dist as D, workloads as W
+    rows = []
+    w0 = W.describe("tape_stress", total_items, rank=rank, world=world, steps=33)
+    for steps in (33, 333, 3333):
+        try:
+            w = W.tape_stress_with_steps(w0, steps)
+            k = W.bind(ctx, w)
+            P = w.nparams
+            th = torch.from_numpy(np.ascontiguousarray(w.theta)).to(dev)
+            obj = D.from_kernel(k, w, dev, comm=comm) if world > 1 else None
+            res = torch.zeros(P + 3, dtype=torch.float64, device=dev)
+
+            def step():
+                nonlocal res
+                if world == 1:
+                    k.eval_device(th.data_ptr(), P, res.data_ptr())
+                else:
+                    res = obj.eval_device(th)
+            step()
+            torch.cuda.synchronize(dev)
+            k.check()
+            reps = 2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            for _ in range(reps):
+                step()
+            e1.record(stream)
+            e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+            sx = torch.tensor([float(np.sum(w.d0))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(sx)
+            ms = float(t.item())
+            out = res.cpu().numpy()
+            f_ref, g_ref = tape_stress_closed_form(float(sx.item()), steps, P)
+            err = max(abs(out[P] - f_ref) / abs(f_ref), float(np.max(np.abs(out[:P] - g_ref)) / np.abs(g_ref).max()))
+            slots = (4 * steps + 1) * total_items
+            cells = (2 * steps + 1) * total_items
+            alg = 24 * slots + 8 * total_items
+            minimal = 2 * (8 * cells + slots // 4) + 8 * total_items
+            st = k.stats()
+            rows.append({"workload": f"config 5: tape stress, {total_items:.0e} work-items x {3 * steps + 1} operators, {world} GPU(s)",
+                         "ad_ops_per_work_item": 3 * steps + 1, "work_items": total_items, "n_gpus": world, "ms_per_eval": ms,
+                         "evals_per_s": 1e3 / ms, "algorithmic_TB": alg / 1e12, "arena_bytes_per_gpu": st["arena_bytes"],
+                         "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                                      "frac": alg / (ms * 1e-3) / 1e9 / (peak * world),
+                                      "minimal_record_frac": minimal / (ms * 1e-3) / 1e9 / (peak * world)},
+                         "parity_rel_err": err, "parity_against": "closed form"})
+            k.free()
+        except Exception as e:  # noqa: BLE001
+            rows.append({"workload": f"config 5: tape stress x {3 * steps + 1} operators", "error": f"{type(e).__name__}: {e}"[:300]})
+        torch.cuda.synchronize(dev)
+    return rows
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -198,6 +425,9 @@ def main():
     ap.add_argument("--n", type=int, default=10_000_000)
     ap.add_argument("--tape-steps", type=int, default=333, help="tape_stress: recurrence steps (3 ops each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the rows for the other BASELINE configs (extra.*)")
+    ap.add_argument("--config5-items", type=int, default=100_000_000, help="work-items of the extra config-5 rows")
+    ap.add_argument("--write-golden", action="store_true", help="N = 1: store f and grad as tests/golden/bench_<workload>_<n>.json")
     ap.add_argument("--acc", default="auto")
     ap.add_argument("--tape", default="auto")
     ap.add_argument("--window", type=int, default=0)
@@ -221,17 +451,19 @@ def main():
     config = {"workload": f"{args.workload} ({'BASELINE config 4: ' if args.workload == 'catch_at_age' else ''}"
                           f"{n} observations x {full.nparams} parameters)",
               "n_obs": n, "n_params": full.nparams,
-              "parallelism": f"observations sharded contiguously over {args.gpus} GPU(s)"
-                             + (f", one {args.allreduce} all-reduce of [grad, sum, ops, slots] per evaluation"
-                                if args.gpus > 1 else "")}
+              "l2": "flushed (256 MiB write) before every timed step",
+              "parallelism": f"observations sharded over {args.gpus} GPU(s)"
+                             + (", one all-reduce of [grad, sum, ops, slots] per evaluation" if args.gpus > 1 else "")}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
         rate, info = cpu_eval_rate(args.workload, n, budget_s=150.0, steps=K, warmup=Wm)
+        info["scaled_from_sample"] = info["n_sample"] < n
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": K, "warmup": Wm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
+                "steps": K, "warmup": Wm, "ms_per_step": 1e3 / rate, "ms_per_step_measured_on_sample": info["ms_per_step_sample"],
+                "scaled_from_sample": info["scaled_from_sample"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "cpu_baseline": info,
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -342,6 +574,8 @@ def main():
         t0 = time.perf_counter()
         if world == 1:
             f_host, g_host = k.eval(w.theta)
+        elif comm is not None:
+            f_host, g_host = k.eval_sharded(comm, w.theta)     # ONE call: H2D, one kernel incl. the all-reduce, D2H
         else:
             theta_dev.copy_(theta_host, non_blocking=True)
             step_device()
@@ -390,16 +624,29 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     alg_bytes = w.algorithmic_bytes()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    # DRAM traffic of the same launch from an ncu capture: only valid for the build it was captured with, so the
+    # record carries the library's device-ABI hash and is dropped (traffic = null) when the kernels have changed
     traffic = None
+    traffic_source = None
     try:
         tr = json.load(open(os.path.join(REPO, "profiles", "dram_traffic.json")))
-        key = f"{args.workload}:{n}:{world}"
-        traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+        rec = tr.get(f"{args.workload}:{n}:{world}", {})
+        if rec.get("device_abi") == host.device_abi():
+            traffic = rec.get("dram_bytes_per_launch")
+            traffic_source = rec.get("source")
+        else:
+            traffic_source = "stale: captured with another build of the device code (device_abi differs)"
     except Exception:  # noqa: BLE001
         pass
     stats = k.stats()
+    min_bytes = w.minimal_record_bytes()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "traffic": traffic, "traffic_source": traffic_source, "frac_of_nominal_8TBs": achieved / 8000.0,
+                # the same time against the bytes the round-2 stream really needs (8-byte header per warp row + cells
+                # of non-unit partials only): the old definition counts bytes this build no longer moves
+                "minimal_record_bytes_per_launch": min_bytes,
+                "minimal_record_GBps": min_bytes / (kernel_ms * 1e-3) / 1e9,
+                "minimal_record_frac": min_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
                 # what actually crossed the HBM interface (ncu capture of the same launch) over this run's kernel time
                 "dram_GBps": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9,
                 "dram_frac": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9 / peak,
@@ -407,21 +654,25 @@ def main():
                                  "frac": w.input_bytes / (kernel_ms * 1e-3) / 1e9 / peak}, "kernel": f"{w.kernel}__entry (fused record+sweep+block reduce)",
                 "kernel_ms": kernel_ms, "kernel_ms_by_rank": kernel_ms_by_rank, "kernel_launches_timed": kernel_launches,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "algorithmic bytes = 24 B x operand slots + inputs + 8(P+1) (SURVEY 8d); the arena of "
-                        "resident warps can stay L2 resident for short tapes, so frac may exceed 1 (see traffic)"}
+                "note": "achieved / frac use SURVEY 8(d)'s definition (24 B x operand slots + inputs + 8(P+1)), which is what "
+                        "round 1 moved; the round-2 stream stores a warp-uniform row once per WARP and no cell for +1/-1 "
+                        "partials (minimal_record_*), and short tapes stay L2 resident (traffic), so the kernel is bound by "
+                        "instruction issue, not by HBM: see profiles/"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(config, ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
+            # identical in both arms (the driver compares them); the launch shape of this arm is in `launch`
+            "config": config,
+            "launch": dict(ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
                            l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
-                           tape_tier=args.tape, acc_mode=args.acc),
+                           tape_tier=stats["tape_tier"], acc_mode=args.acc, launches_per_eval=k.launches_per_eval),
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    # N = 1: ad4cl_cuda_eval moves P host-packed ad_variables (16 B each) up and P+4 doubles down;
-                    # N > 1: P doubles up, the all-reduced P+3 doubles down
-                    "h2d_bytes_per_step": 16 * P if world == 1 else 8 * P,
-                    "d2h_bytes_per_step": 8 * (P + 4) if world == 1 else 8 * (P + 3),
+                    # ad4cl_cuda_eval / ad4cl_cuda_eval_sharded: P doubles up, [grad, f, ops, slots, status] down,
+                    # replayed as one CUDA graph (H2D, ONE kernel, D2H)
+                    "h2d_bytes_per_step": 8 * P,
+                    "d2h_bytes_per_step": 8 * (P + 4),
                     "note": "observations device-resident across evaluations as in simple.cpp:206-230; "
                             "theta up / [grad,f,ops,slots(,status)] down every step",
                     "with_data_upload": e2e_cold},
@@ -431,8 +682,37 @@ def main():
             "ad_ops_per_s": float(st_result[P + 1]) * value,
             "objective": float(st_result[P])}
 
+    # ---- parity of this run's result against the committed N = 1 result of the same workload (hex floats):
+    # driver-visible evidence that the sharded path (fused one-shot all-reduce included) computes the same numbers
+    gold_path = os.path.join(REPO, "tests", "golden", f"bench_{args.workload}_{n}.json")
+    if args.write_golden and rank == 0 and world == 1:
+        json.dump({"workload": args.workload, "n": n, "f": float(st_result[P]).hex(),
+                   "grad": [float(v).hex() for v in st_result[:P]], "device_abi": host.device_abi(),
+                   "note": "python bench.py --write-golden on 1 B200"}, open(gold_path, "w"), indent=1)
+    parity_check = {"status": "no golden"}
+    try:
+        gold = json.load(open(gold_path))
+        f_ref = float.fromhex(gold["f"])
+        g_ref = np.array([float.fromhex(v) for v in gold["grad"]])
+        ef = abs(float(st_result[P]) - f_ref) / abs(f_ref)
+        eg = float(np.max(np.abs(st_result[:P] - g_ref)) / np.abs(g_ref).max())
+        parity_check = {"status": "ok" if max(ef, eg) <= 1e-12 else "FAILED", "rel_err_f": ef, "rel_err_grad": eg,
+                        "against": f"tests/golden/{os.path.basename(gold_path)} (1-GPU result)", "tolerance": 1e-12}
+    except FileNotFoundError:
+        pass
+    line["parity_check"] = parity_check
+
+    # ---- every other BASELINE config (short runs, outside the headline's timed region)
+    if not args.no_extra and args.workload == "catch_at_age":
+        extra = {}
+        if world == 1 and rank == 0:
+            extra["configs"] = extra_configs(ctx, dev, stream, flush, peak, with_oracle=not args.no_cpu_baseline)
+        extra["config5_at_1e8"] = config5_sharded(ctx, dev, stream, flush, peak, rank, world, comm, args.config5_items)
+        line["extra"] = extra
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, info = cpu_eval_rate(args.workload, n, budget_s=25.0)
+        info["scaled_from_sample"] = info["n_sample"] < n
         info["opencl_on_this_gpu"] = opencl_reference_rate(args.workload, n, min(info["n_sample"], 1_000_000))
         line["cpu_baseline"] = info
     if comm is not None:

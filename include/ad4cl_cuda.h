@@ -68,8 +68,13 @@ enum {
 /* tape tier */
 enum {
     AD4CL_TAPE_AUTO = -1,
-    AD4CL_TAPE_HBM = 0,     /* thread-interleaved arena in HBM (L2-resident when small) */
-    AD4CL_TAPE_SHARED = 1   /* rows in shared memory (short tapes) */
+    AD4CL_TAPE_HBM = 0,     /* per-warp streams in an HBM arena (L2-resident when small) */
+    AD4CL_TAPE_SHARED = 1,  /* the same streams in shared memory (short tapes) */
+    AD4CL_TAPE_REGISTER = 2 /* short straight-line objectives: tape, adjoints and gradient accumulators are
+                               REGISTERS of the thread (an instance of the kernel compiled for the number of
+                               independents and the loop-bounding integer argument; the intent of the
+                               reference's private stacks, ad.cl:51-57, 91-97).  AUTO picks it whenever such
+                               an instance exists and was fully scalarised, else AD4CL_TAPE_HBM. */
 };
 
 /* Round 1: L2 prefetch of tape rows in the sweep, auto-tuned.  Since round 2 the tape of a warp is a
@@ -111,6 +116,7 @@ typedef struct ad4cl_eval_stats {
     size_t arena_bytes;
     float kernel_ms;        /* device time of the last evaluation (both launches) */
     int sweep_prefetch;     /* always 0 since round 2 */
+    int tape_tier;          /* the AD4CL_TAPE_* tier in use (what AUTO resolved to) */
 } ad4cl_eval_stats;
 
 int ad4cl_cuda_init(int device, ad4cl_context** ctx);
@@ -193,6 +199,11 @@ int ad4cl_cuda_eval(ad4cl_kernel* kernel, const double* theta, int nparams, doub
  */
 int ad4cl_cuda_eval_device(ad4cl_kernel* kernel, const double* theta_dev, int nparams,
         double* result_dev, int want_gradient, int apply_epilogue);
+/* the same, predicated on device memory: skipped when *skip_dev != 0 at EXECUTION time (for evaluations
+   captured in a CUDA graph behind a device-side decision, e.g. an optimiser that has converged) */
+int ad4cl_cuda_eval_device_if(ad4cl_kernel* kernel, const double* theta_dev, int nparams,
+        double* result_dev, int want_gradient, int apply_epilogue, const int* skip_dev);
+ad4cl_context* ad4cl_cuda_kernel_context(ad4cl_kernel* kernel);
 /* synchronise the stream and report tape overflow / window errors of queued evaluations */
 int ad4cl_cuda_check(ad4cl_kernel* kernel);
 int ad4cl_cuda_last_stats(ad4cl_kernel* kernel, ad4cl_eval_stats* stats);
@@ -244,6 +255,17 @@ typedef struct ad4cl_lbfgs_result {
 
 int ad4cl_cuda_lbfgs_options_default(ad4cl_lbfgs_options* options);
 int ad4cl_cuda_minimize_lbfgs(ad4cl_kernel* kernel, double* theta, int number_of_parameters,
+        const ad4cl_lbfgs_options* options, ad4cl_lbfgs_result* result);
+/*
+ * The same minimiser DEVICE RESIDENT (what lbfgs_parameters_g / lbfgs_update_g,
+ * ad.cl:99-127, were declared for): parameters, history pairs and the line-search state live in device
+ * memory; between two evaluations ONE single-CTA kernel (lbfgs_update) takes the Armijo decision, updates
+ * the history, runs the two-loop recursion and writes the next trial point where the next evaluation reads
+ * it.  The fit is replayed as CUDA graphs of 128 (evaluation, update) pairs: no host synchronisation and no
+ * PCIe traffic between evaluations; once converged the remaining evaluations of the graph skip themselves
+ * (ad4cl_cuda_eval_device_if).  Same options, same result fields; theta: start point in, minimiser out.
+ */
+int ad4cl_cuda_minimize_lbfgs_device(ad4cl_kernel* kernel, double* theta, int number_of_parameters,
         const ad4cl_lbfgs_options* options, ad4cl_lbfgs_result* result);
 
 /*
@@ -302,6 +324,20 @@ int ad4cl_cuda_eval_sharded(ad4cl_kernel* kernel, ad4cl_comm* comm, const double
         double* f, double* grad);
 int ad4cl_cuda_eval_device_sharded(ad4cl_kernel* kernel, ad4cl_comm* comm, const double* theta_dev, int nparams,
         double* result_dev, int want_gradient);
+/*
+ * General epilogues / non-uniform seeds.  The reference's sweep seeds only the LAST tape
+ * entry (ad4cl.h:786) and its examples only ever reduce with f = h(sum_i out_i) (simple.cpp:357-365).  For
+ * an objective f = h(out_1, .., out_n) that is not of that form, evaluate in two passes -- nothing is
+ * retained between them, the tape still never leaves the SM / L2:
+ *   pass 1   out_values_dev != NULL, grad == NULL: every work-item stores out_i.value (indexed like the
+ *            kernel's own out[]; device memory, n doubles).  The caller computes the seeds
+ *            s_i = dh / d out_i from them (on the device or the host).
+ *   pass 2   seeds_dev != NULL, grad != NULL: work-item i's sweep starts from s_i instead of 1, so
+ *            grad = sum_i s_i * d out_i / d theta = the gradient of f.
+ * *sum receives sum_i out_i either way (no epilogue is applied).  theta and grad are host memory.
+ */
+int ad4cl_cuda_eval_general(ad4cl_kernel* kernel, const double* theta, int nparams, double* out_values_dev,
+        const double* seeds_dev, double* sum, double* grad);
 /* kernel launches the last evaluation of this kernel enqueued (1 unless AD4CL_ACC_GLOBAL) */
 int ad4cl_cuda_launches_per_eval(ad4cl_kernel* kernel);
 

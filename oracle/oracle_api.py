@@ -126,6 +126,22 @@ class Reference(_Base):
         return {"value": v.value, "id": rid.value, "lhs": lhs.value,
                 "size": e.size, "eid": e.id, "dx": (e.dx0, e.dx1), "ids": (e.id0, e.id1)}
 
+    def eval_weighted_log(self, name, theta, d0, d1, size, weights, i0=0, i1=0, ops_per_item=64, shift=0.0):
+        """f = sum_i w_i log(out_i + shift) recorded with the reference's host operators on top of the kernel's out[]
+        and swept by compute_gradient -> dict(f, grad, out)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        d0 = None if d0 is None else np.ascontiguousarray(d0, dtype=np.float64)
+        d1 = None if d1 is None else np.ascontiguousarray(d1, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        cap = int(ops_per_item + 5) * max(size, 1) + 64
+        f = c_double()
+        grad, out = np.zeros(len(theta)), np.zeros(size)
+        rc = self.lib.ref_eval_weighted_log(name.encode(), len(theta), _p(theta), _p(d0), _p(d1), size, i0, i1, size,
+                                            _p(w), c_double(shift), c_longlong(cap), byref(f), _p(grad), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"ref_eval_weighted_log rc={rc}")
+        return {"f": f.value, "grad": grad, "out": out}
+
     def eval_simple(self, variant, a, b, x, y, *, global_size=None, threads=1):
         """The reference's own config-1 kernels: variant 0 kernel.cl, 1 simple.cl, 2 host AD()."""
         x = np.ascontiguousarray(x, dtype=np.float64)

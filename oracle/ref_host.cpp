@@ -189,6 +189,56 @@ int ref_eval_objective(const char* name, int nparams, const double* theta,
 }
 
 /*
+ * A NON-UNIFORM-SEED epilogue on the reference's own runtime: the kernel's out[] as above,
+ * then the host tape records  f = sum_i w_i * log(out_i + shift)  with the reference's ad_plus_vd, ad_log,
+ * ad_times_dv and ad_plus_eq_v (ad4cl.h:131, 651, 368, 186) and compute_gradient (ad4cl.h:775-802) sweeps the
+ * whole stack.  d f / d out_i = w_i / (out_i + shift) differs per work-item: the case the (n/2) log sum
+ * epilogue never exercises.  (ad_plus_vd has the reference's Q4 defect; use the patched build.)
+ */
+int ref_eval_weighted_log(const char* name, int nparams, const double* theta,
+        double* d0, double* d1, int size, int i0, int i1, int global_size, const double* weights, double shift,
+        long long stack_entries, double* f, double* grad, double* out_values) {
+    host_gs_t gs_s;
+    host_gs_t* gs = &gs_s;
+    gs->current_variable_id = 0;
+    gs->stack_current = 0;
+    gs->recording = 1;
+    gs->counter = 0;
+    entry_t* stack = (entry_t*) calloc((size_t) stack_entries, sizeof (entry_t));
+    if (!stack) return -2;
+    gs->gradient_stack = stack;
+    std::vector<var_t> th(nparams);
+    for (int p = 0; p < nparams; p++) ad_init_var(gs, &th[p], theta[p]);
+    std::vector<var_t> out(size > 0 ? size : 1);
+    dev_gs_image img;
+    img.write(gs);
+    int rc = ref_launch_objective(name, img.bytes, stack, th.data(), d0, d1, out.data(), size, i0, i1, global_size, 1);
+    if (rc != 0) {
+        free(stack);
+        return rc;
+    }
+    img.read(gs);
+    gs->gradient_stack = stack;
+    gpu_restore(gs);
+    if ((long long) gs->stack_current + 4LL * size + 2 > stack_entries) {
+        free(stack);
+        return -3;
+    }
+    var_t sum = {.value = 0.0, .id = gs->current_variable_id++};
+    for (int i = 0; i < size; i++) {
+        if (out_values) out_values[i] = out[i].value;
+        ad_plus_eq_v(gs, &sum, ad_times_dv(gs, weights[i], ad_log(gs, ad_plus_vd(gs, out[i], shift))));
+    }
+    int gsize = 0;
+    double* g = compute_gradient(*gs, gsize);
+    *f = sum.value;
+    for (int p = 0; p < nparams; p++) grad[p] = g[p];
+    free(g);
+    free(stack);
+    return 0;
+}
+
+/*
  * test/matrix: C = A*B on n x n ad_variables, then the host sum of C
  * (matrix_mul.cpp:253-261).  A gets ids 0..n^2-1, B ids n^2..2n^2-1
  * (matrix_mul.cpp:84-90).

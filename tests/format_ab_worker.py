@@ -27,7 +27,8 @@ def main():
         f, g = k.eval(w.theta)
         st = k.stats()
         k.free()
-        print(name, n, float(f).hex(), " ".join(float(x).hex() for x in np.asarray(g)), int(st["ops"]), int(st["slots"]))
+        kind = "exact" if len(w.theta) <= 16 and cfg.get("acc", "auto") in ("auto", "thread") else "close"
+        print(name, n, kind, float(f).hex(), " ".join(float(x).hex() for x in np.asarray(g)), int(st["ops"]), int(st["slots"]))
     ctx.close()
 
 

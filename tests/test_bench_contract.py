@@ -42,13 +42,22 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = run_bench("--n", "2000000", "--steps", "5", "--warmup", "3")
+    d = run_bench("--n", "2000000", "--steps", "5", "--warmup", "3", "--config5-items", "1000000")
     assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks"} <= set(d) and "impl" not in d
-    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["gpu_launches"] == 15
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["gpu_launches"] == 5
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert 0.3 < r["frac"] < 1.5 and r["kernel_launches_timed"] == 5
-    assert d["e2e"]["h2d_bytes_per_step"] == 1600 and d["e2e"]["d2h_bytes_per_step"] == 832
+    assert 0.3 < r["frac"] < 3.0 and r["kernel_launches_timed"] == 5
+    assert d["e2e"]["h2d_bytes_per_step"] == 800 and d["e2e"]["d2h_bytes_per_step"] == 832
+    assert d["launch"]["launches_per_eval"] == 1 and d["launch"]["tape_tier"] == "hbm"
+    assert d["parity_check"]["status"] in ("ok", "no golden")
+    rows = d["extra"]["configs"]                             # every other BASELINE config, one row each
+    assert len(rows) >= 8 and not [r for r in rows if "error" in r], rows
+    for r in rows:
+        assert r["parity_rel_err"] is not None and r["parity_rel_err"] <= 1e-12, r
+        assert r["roofline"]["frac"] > 0
+    assert {r["tape_tier"] for r in rows if r["kernel"] in ("linreg2_p", "regression_linear", "regression_logistic")} == {"register"}
+    assert len(d["extra"]["config5_at_1e8"]) == 3 and all(r["parity_rel_err"] <= 1e-12 for r in d["extra"]["config5_at_1e8"])
     assert 0.5 * d["value"] < d["e2e"]["value"] <= 1.05 * d["value"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] < d["value"] / 100
     ocl = d["cpu_baseline"]["opencl_on_this_gpu"]            # context: the unmodified OpenCL path on this GPU, if it has one

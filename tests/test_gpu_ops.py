@@ -148,7 +148,7 @@ def test_var_operators_are_the_function_calls(ctx):
     out = []
     for name in ("regression_logistic", "regression_logistic_var"):
         w.kernel = name
-        k = W.bind(ctx, w)
+        k = W.bind(ctx, w, tape="hbm")      # the function-call form also has a register-tier instance: compare like with like
         out.append(k.eval(w.theta))
         k.free()
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])

@@ -14,8 +14,8 @@ REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 GOLD = os.path.join(REPO, "tests", "golden")
 
 
-def build(src, out, quirks=None, link=False):
-    cmd = ["/usr/bin/g++", "-O2", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), src, "-o", out]
+def build(src, out, quirks=None, link=False, extra=()):
+    cmd = ["/usr/bin/g++", "-O2", "-Wall", "-Werror", *extra, "-I", os.path.join(REPO, "include"), src, "-o", out]
     if quirks is not None:
         cmd.insert(1, f"-DAD4CL_REFERENCE_QUIRKS={int(quirks)}")
     if link:
@@ -81,6 +81,27 @@ def test_main_cpp_loop_on_cuda(tmp_path, oracle_api):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [1, 2, 3])
+def test_cpp_host_drives_the_sharded_call(tmp_path, ranks):
+    """examples/sharded_cuda.cpp: a g++-compiled host creates one context + communicator per rank in ONE process
+    (ad4cl_cuda_comm_create_local) and calls ad4cl_cuda_eval_sharded from one thread per rank; every rank must
+    print the same bits, equal to the single-GPU evaluation of the whole problem to 1e-12, from ONE launch."""
+    import re
+    exe = str(tmp_path / "sharded_cuda")
+    build(os.path.join(REPO, "examples", "sharded_cuda.cpp"), exe, link=True, extra=["-pthread"])
+    out = subprocess.run([exe, "200003", str(ranks), "4"], capture_output=True, text=True, check=True, timeout=120).stdout
+    num = r"(-?\d+\.?\d*(?:e[-+]?\d+)?)"
+    rows = re.findall(r"rank \d+ of \d+ on device \d+: f = %s  df/da = %s  df/db = %s  launches/eval = (\d+)" % (num, num, num), out)
+    single = re.search(r"single GPU: f = %s  df/da = %s  df/db = %s" % (num, num, num), out)
+    assert len(rows) == ranks and single, out
+    f1, a1, b1 = (float(v) for v in single.groups())
+    for f, a, b, launches in rows:
+        assert (f, a, b) == rows[0][:3] and int(launches) == 1
+        assert abs(float(f) - f1) <= 1e-12 * abs(f1)
+        assert abs(float(a) - a1) <= 1e-12 * max(abs(a1), abs(b1)) and abs(float(b) - b1) <= 1e-12 * max(abs(a1), abs(b1))
+
+
+@pytest.mark.gpu
 def test_optimiser_drives_the_cuda_path():
     """examples/fit_catch_at_age.py: L-BFGS over ad4cl_cuda_eval recovers the parameters the
     synthetic catch was generated from (the soft-golden style of the reference's .par files:
@@ -115,6 +136,28 @@ def test_library_lbfgs_recovers_the_regression_line(ctx):
     assert res["converged"] in (1, 2) and res["evaluations"] < 200
     assert abs(theta[0] - a_ls) < 1e-6 and abs(theta[1] - b_ls) < 1e-5
     assert abs(theta[0] - 2.0) < 0.01 and abs(theta[1] - 4.0) < 0.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n", [("linreg2_simple", 100003), ("regression_logistic", 50000), ("catch_at_age", 120000)])
+def test_device_resident_lbfgs_equals_the_host_loop(ctx, name, n):
+    """ad4cl_cuda_minimize_lbfgs_device (lbfgs_parameters_g / lbfgs_update_g of ad.cl:99-127, defined): the same
+    algorithm as the host loop, run as CUDA graphs of (evaluation, update) pairs with no host round trip
+    between evaluations.  Same minimum, same iteration / evaluation counts up to the rounding of the
+    dot products; the fit itself is bit-reproducible."""
+    from ad4cl_b200 import workloads as W
+    w = W.describe(name, n)
+    k = W.bind(ctx, w)
+    opts = dict(max_iterations=300, gradient_tolerance=1e-6 if name != "catch_at_age" else 1e-3)
+    th_h, res_h = k.minimize(w.theta, device_resident=False, **opts)
+    th_d, res_d = k.minimize(w.theta, device_resident=True, **opts)
+    th_d2, res_d2 = k.minimize(w.theta, device_resident=True, **opts)
+    k.free()
+    assert res_d["converged"] in (1, 2) and res_h["converged"] in (1, 2), (res_d, res_h)
+    assert np.array_equal(th_d, th_d2) and res_d == res_d2
+    assert abs(res_d["f"] - res_h["f"]) <= 1e-9 * abs(res_h["f"])
+    assert np.abs(th_d - th_h).max() <= 1e-4 * max(1.0, np.abs(th_h).max())
+    assert abs(res_d["evaluations"] - res_h["evaluations"]) <= max(3, res_h["evaluations"] // 5)
 
 
 @pytest.mark.gpu
