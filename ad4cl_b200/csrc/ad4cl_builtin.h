@@ -1,8 +1,9 @@
 #pragma once
-/* one row per ahead-of-time compiled kernel: name, its entry per accumulator mode (_m0/_m1/_m2), signature */
+/* one row per ahead-of-time compiled kernel: name, its entries [recorder: 0 uniform (_u), 1 lane (_m)]
+   [accumulator mode 0..2], signature */
 struct ad4cl_builtin_row {
     const char* name;
-    const void* entry[3];
+    const void* entry[2][3];
     const char* signature;
 };
 /* one row per register-tier instance (builtin_static.cu): valid for exactly `nparams` independents bound as

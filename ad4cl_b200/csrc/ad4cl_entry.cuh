@@ -70,6 +70,7 @@ struct LaunchInfo {
        Pass 1 (out_values set, objective only): every work-item stores out_i.value.  The caller turns them
        into seeds s_i = dh/d out_i.  Pass 2 (seeds set): the sweep of work-item i starts from s_i instead of 1,
        so the reduced gradient is sum_i s_i * d out_i / d theta.  Both indexed like the kernel's own out[]. */
+    int sweep_prefetch;     /* general sweep: L2 prefetch two batches ahead */
     const double* seeds;
     double* out_values;
     long long n_user;       /* work-items the caller configured (the NDRange is padded to whole work-groups) */
@@ -345,7 +346,12 @@ __device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&&
     }
 }
 #else
-template <int MODE, typename Body>
+/* POLICY = kRecordGeneral: the LANE kernel -- one copy of the user kernel, the general recorder only (the
+   round-1 code path, with its instruction-cache footprint).  POLICY = kRecordUniform: the UNIFORM kernel --
+   the optimistic uniform recorder first, a second copy of the user kernel with the general recorder for the
+   work-items (and, after three failures in a row, the warps) it cannot take.  Which kernel a launch uses is
+   the shim's choice (AD4CL_RECORDER_*). */
+template <int MODE, int POLICY, typename Body>
 __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) {
     if (L.skip != nullptr && *reinterpret_cast<const volatile int*> (L.skip) != 0) return;
     const int B = blockDim.x;
@@ -439,9 +445,9 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         const bool mine = gid0 < L.g0_user && out_index < L.n_user;
         const double seed = L.seeds == nullptr ? 1.0 : (mine ? L.seeds[out_index] : 0.0);
         bool general = true;
-#if !AD4CL_BODY_HAS_BARRIER && !AD4CL_FORCE_GENERAL
-        general = opt_fails >= 3 || L.recording != 1 || L.retain_meta != nullptr;
-        if (!general) {
+#if !AD4CL_BODY_HAS_BARRIER
+        if (POLICY == kRecordUniform) general = opt_fails >= 3 || L.recording != 1 || L.retain_meta != nullptr;
+        if (POLICY == kRecordUniform && !general) {
             /* ---- first copy of the user kernel: the uniform recorder ---- */
             tape_begin(tape, kRecordUniform);
             body(&gs, &outv - out_index);
@@ -474,9 +480,10 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
                 m[2] = (double) (tape.next_id - tape.first_temp);
             } else if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
                 /* a thread whose tape overflowed skips the sweep (the host reports the error) */
-                tape.status |= tape_sweep_general<MODE>(tape.cells, tape.lane_words, tape.far_adj,
+                if (MODE == kAccWarp) param_flush(T.warp_acc, pend);   /* keep the order of the additions fixed */
+                tape.status |= tape_sweep_general<MODE>(tape.rows, tape.id_off, tape.far_adj,
                         tape.next_id - tape.first_temp, tape.first_temp, tape.wm1, outv.id, seed, T,
-                        (int) L.cap_slots + kGuardRows);
+                        (int) L.cap_slots + kGuardRows, L.sweep_prefetch);
             }
         }
         sum += outv.value;
@@ -575,12 +582,16 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     }
 #endif
 #if !AD4CL_TAPE_STATIC
-#define AD4CL_OBJECTIVE_ENTRY_MODE(NAME, MODE, PARAMS, ARGS)                               \
+/* one __global__ function per (recorder policy, accumulator mode), so a launch only brings the code it uses
+   into the instruction cache: NAME__entry<suffix>_m0/_m1/_m2 (LANE kernel) and _u0/_u1/_u2 (UNIFORM kernel;
+   not built for kernels with work-group barriers, which cannot be re-run by a single warp) */
+#define AD4CL_ENTRY_NAME2(NAME, TAG, MODE) AD4CL_CAT4(NAME, __entry, AD4CL_ENTRY_SUFFIX, _##TAG##MODE)
+#define AD4CL_OBJECTIVE_ENTRY_MODE(NAME, MODE, POLICY, TAG, PARAMS, ARGS)                  \
     extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK, AD4CL_MIN_BLOCKS)        \
-    AD4CL_ENTRY_NAME(NAME, MODE)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
-        /* always_inline: the body is instantiated twice (uniform and general recorder), and only inlined  \
-           copies let the compiler keep the tape cursor in registers and fold the recorder mode */        \
-        ad4cl::run_objective<MODE>(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out)      \
+    AD4CL_ENTRY_NAME2(NAME, TAG, MODE)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {  \
+        /* always_inline: the body may be instantiated twice (uniform and general recorder), and only     \
+           inlined copies let the compiler keep the tape cursor in registers and fold the recorder mode */ \
+        ad4cl::run_objective<MODE, POLICY>(L, [&](struct ad_gradient_structure* gs, struct ad_variable* out) \
                 __attribute__((always_inline)) {                                           \
             struct ad_entry* gradient_stack = nullptr;                                     \
             (void) gradient_stack;                                                         \
@@ -588,7 +599,10 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
         });                                                                                \
     }
 #define AD4CL_OBJECTIVE_ENTRY(NAME, PARAMS, ARGS)                                         \
-    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 0, PARAMS, ARGS)                                      \
-    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 1, PARAMS, ARGS)                                      \
-    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 2, PARAMS, ARGS)
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 0, ad4cl::kRecordGeneral, m, PARAMS, ARGS)            \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 1, ad4cl::kRecordGeneral, m, PARAMS, ARGS)            \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 2, ad4cl::kRecordGeneral, m, PARAMS, ARGS)            \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 0, ad4cl::kRecordUniform, u, PARAMS, ARGS)            \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 1, ad4cl::kRecordUniform, u, PARAMS, ARGS)            \
+    AD4CL_OBJECTIVE_ENTRY_MODE(NAME, 2, ad4cl::kRecordUniform, u, PARAMS, ARGS)
 #endif /* !AD4CL_TAPE_STATIC */

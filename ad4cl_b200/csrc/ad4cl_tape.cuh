@@ -73,6 +73,8 @@ constexpr int kNoId = (int) 0x80000000u;
 /* second header word (uniform recorder): byte offset of the slot's cell in the lane's cell column */
 
 constexpr int kHdrBytes = 8;
+constexpr int kRowBytes = 384;              /* general recorder: 32 lanes x (8 B partial + 4 B id word) */
+constexpr int kRowIdOffset = 256;
 constexpr int kCellRowBytes = 256;          /* 32 lanes x 8 B */
 constexpr int kLaneWordRowBytes = 128;      /* 32 lanes x 4 B */
 constexpr int kFarRowBytes = 256;           /* far adjoints: 32 lanes x 8 B per slot index */
@@ -94,13 +96,10 @@ enum Status : int {
 #ifndef AD4CL_DEBUG_BOUNDS
 #define AD4CL_DEBUG_BOUNDS 0
 #endif
-/* A/B switch (make general -> libad4cl_cuda_general.so, tests/test_gpu_format_ab.py): 1 never tries the
-   uniform recorder, i.e. the per-lane format and the general sweep everywhere.  Per lane the tape
-   arithmetic is the same in both formats; only the order in which an independent's contributions are
-   summed over the warp differs (pairs in the uniform sweep), so results agree to rounding, and bit for
-   bit with per-thread accumulators. */
-#ifndef AD4CL_FORCE_GENERAL
-#define AD4CL_FORCE_GENERAL 0
+/* A/B switch for the general sweep: 0 removes the per-batch vote and the warp-uniform batch body (every
+   lane always classifies its own id word, as in round 1) */
+#ifndef AD4CL_LANE_UNIFORM_BATCHES
+#define AD4CL_LANE_UNIFORM_BATCHES 1
 #endif
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -324,8 +323,11 @@ __device__ __forceinline__ void tape_sweep_static(const ThreadTape& t, int out_i
  *                   sets the sticky `bad` flag, and the work-item is then recorded AGAIN by the general
  *                   recorder.  Re-running the user kernel is safe because its only effects are the tape
  *                   and the virtual out (kernels with work-group barriers are built general-only).
- *   kRecordGeneral  every lane keeps its own id word (lane-word plane, 128 B per row) and its own
- *                   partial (cell row + 2): any control flow, any ids, far operands.
+ *   kRecordGeneral  the round-1 stream: every lane keeps its own id word and its own partial, one
+ *                   384-byte row per slot [partials of the 32 lanes : 256 B][id words : 128 B], so a push
+ *                   is two coalesced stores at one running pointer: any control flow, any ids.  Its sweep
+ *                   (tape_sweep_general) still notices, batch by batch, when the 32 id words agree, and then
+ *                   classifies on warp-uniform branches and reduces independents' contributions in pairs.
  */
 constexpr int kRecordUniform = 0;
 constexpr int kRecordGeneral = 1;
@@ -335,7 +337,9 @@ struct ThreadTape {
     char* hdr;            /* header plane of this warp, row 0 (the same address in all lanes) */
     char* hdr_cur;        /* uniform recorder: header of the next free row */
     char* cells;          /* this lane's cell column: cell k at cells + 256 k */
-    char* lane_words;     /* this lane's id-word column (general recorder): row r at lane_words + 128 r */
+    char* rows;           /* general recorder: this lane's partial in row 0 (row stride kRowBytes) */
+    char* cur;            /* general recorder: this lane's partial in the next free row */
+    int id_off;           /* general recorder: byte offset from a row's partial to its id word, this lane */
     char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
     unsigned cell_off;    /* uniform recorder: byte offset of this lane's next free cell */
     int next_id;          /* first_temp + index of the next free row */
@@ -358,7 +362,11 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
     t.hdr = warp_region;
     t.hdr_cur = warp_region;
     t.cells = warp_region + lay.off_cells + lane * 8;
-    t.lane_words = warp_region + lay.off_lane_words + lane * 4;
+    /* the general recorder's rows share the space of the cell plane and the (former) lane-word plane:
+       (rows + 2) * 256 + rows * 128 = 512 + rows * 384 bytes */
+    t.rows = t.cells + kUnitCells * kCellRowBytes;
+    t.cur = t.rows;
+    t.id_off = kRowIdOffset - lane * 4;
     t.far_adj = far ? warp_region + lay.off_far + lane * 8 : nullptr;
     t.cell_off = kUnitCells * kCellRowBytes;
     t.next_id = first_temp;
@@ -380,6 +388,7 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
 __device__ __forceinline__ void tape_begin(ThreadTape& t, int mode) {
     t.mode = mode;
     t.hdr_cur = t.hdr;
+    t.cur = t.rows;
     t.cell_off = kUnitCells * kCellRowBytes;
     t.next_id = t.first_temp;
     t.nops = 0;
@@ -408,12 +417,12 @@ __device__ __forceinline__ unsigned long long tape_uniform_key(const ThreadTape&
  *     constant operand instead of an id the sweep would follow out of the arena.
  * Returns the id word in the low half and Status bits in the high half.
  */
-static __device__ __noinline__ unsigned long long tape_classify_rare(char* lane_words, const char* far_adj,
+static __device__ __noinline__ unsigned long long tape_classify_rare(char* rows, int id_off, const char* far_adj,
         int id, int first_temp, int row, int flags) {
     const int pos = id - first_temp;
     if (pos < 0 || pos >= row) return (unsigned) (flags | kNopFlag);
     if (far_adj == nullptr) return ((unsigned long long) kErrWindow << 32) | (unsigned) (flags | kNopFlag);
-    atomicOr(reinterpret_cast<int*> (lane_words + (size_t) pos * kLaneWordRowBytes), kHasFarFlag);
+    atomicOr(reinterpret_cast<int*> (rows + (size_t) pos * kRowBytes + id_off), kHasFarFlag);
     return (unsigned) (pos | flags | kFarFlag);
 }
 
@@ -431,29 +440,31 @@ static __device__ __noinline__ unsigned long long tape_classify_rare(char* lane_
  */
 template <int UNIT>
 __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int flags) {
+    /* Both recorders advance their cursors UNCONDITIONALLY by compile-time constants: inside a basic block
+       the compiler then addresses consecutive pushes as [cursor + immediate] and updates the cursor once.
+       Capacity is checked once per operator (tape_close_op); the guard rows absorb the last operator. */
     if (t->mode == kRecordUniform) {
         const int word = (flags & kNopFlag) ? flags : (id | flags);
         const bool valid = (flags & kNopFlag) || (unsigned) id < (unsigned) t->next_id;
-        const bool room = t->next_id < t->cap_id;
 #if AD4CL_UNIFORM_HASH
         /* no vote per push: every lane folds its raw word into two independent multiplicative hashes and the
            warp compares them ONCE per work-item (tape_uniform_key).  A lane that skipped a push, pushed in
            another order or pushed another word ends with different hashes, up to a 2^-64 collision. */
         t->h1 = t->h1 * 0x9E3779B1u + (unsigned) word;
         t->h2 = (t->h2 ^ (unsigned) word) * 0x85EBCA6Bu + 0xC2B2AE35u;
-        t->bad |= (!valid || !room) ? 1 : 0;
+        t->bad |= valid ? 0 : 1;
 #else
         const unsigned mask = __activemask();
         int same = 0;
         __match_all_sync(mask, word, &same);
-        t->bad |= (!valid || !same || mask != 0xffffffffu || !room) ? 1 : 0;
+        t->bad |= (!valid || !same || mask != 0xffffffffu) ? 1 : 0;
 #endif
         const unsigned aux = UNIT == 0 ? t->cell_off : (UNIT > 0 ? 0u : (unsigned) kCellRowBytes);
         *reinterpret_cast<int2*> (t->hdr_cur) = make_int2(word, (int) aux);
-        if (UNIT == 0) *reinterpret_cast<double*> (t->cells + t->cell_off) = dx;
-        if (room) { /* a full column stops advancing (guard rows take the stores); `bad` is already set */
-            t->hdr_cur += kHdrBytes;
-            if (UNIT == 0) t->cell_off += kCellRowBytes;
+        t->hdr_cur += kHdrBytes;
+        if (UNIT == 0) {
+            *reinterpret_cast<double*> (t->cells + t->cell_off) = dx;
+            t->cell_off += kCellRowBytes;
         }
         t->next_id++;
     } else {
@@ -463,26 +474,24 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
            at or above the current row and kNoId. */
         const bool reach = (unsigned) (t->next_id - 1 - id) < (unsigned) (t->wm1 - 1);
         int word = (flags & kNopFlag) ? flags : (is_param ? (id | kParamFlag) : (id - t->first_temp)) | flags;
-        const bool room = t->next_id < t->cap_id;
-        const int row = t->next_id - t->first_temp;
         if (!(flags & kNopFlag) && !is_param && !reach) {
-            const unsigned long long r = tape_classify_rare(t->lane_words, t->far_adj, id, t->first_temp, row, flags);
+            const unsigned long long r = tape_classify_rare(t->rows, t->id_off, t->far_adj, id, t->first_temp,
+                    t->next_id - t->first_temp, flags);
             word = (int) (unsigned) r;
             t->status |= (int) (r >> 32);
         }
-        *reinterpret_cast<double*> (t->cells + (size_t) (row + kUnitCells) * kCellRowBytes) = UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0);
-        *reinterpret_cast<int*> (t->lane_words + (size_t) row * kLaneWordRowBytes) = word;
-        /* a full column stays on its guard row and says so (the sweep is skipped, the host reports it) */
-        t->status |= room ? kOk : kErrTapeOverflow;
-        t->next_id += room ? 1 : 0;
+        *reinterpret_cast<double*> (t->cur) = UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0);
+        *reinterpret_cast<int*> (t->cur + t->id_off) = word;
+        t->cur += kRowBytes;
+        t->next_id++;
     }
 }
 
 /*
  * Uniform recorder, after the work-item: turn the raw words id | flags of the `rows` headers into the
  * classified id words the sweep reads (PARAM + id; position of a recent temporary; FAR + position, with
- * HAS_FAR -- one byte store into the low byte of the producer's cell offset, which is always 0 -- on the row
- * that produced the operand).  ONE classification per row for the whole warp, row r by lane r mod 32.
+ * HAS_FAR on the row that produced the operand).  ONE classification per row for the whole warp, row r by
+ * lane r mod 32.
  * Returns non-zero (warp-uniform) when the tape needs the general recorder after all: a far operand with the
  * far plane disabled.  Out of line: runs once per work-item.
  */
@@ -498,19 +507,22 @@ static __device__ __noinline__ int tape_classify_uniform(char* hdr, const char* 
             if (id < first_temp) {
                 word = id | kParamFlag | flags;
             } else {
-                const int pos = id - first_temp;
-                word = pos | flags;
+                word = (id - first_temp) | flags;
                 if (!((unsigned) (first_temp + r - 1 - id) < (unsigned) (wm1 - 1))) { /* beyond the ring's reach */
-                    if (far_adj == nullptr) {
-                        bad = 1;
-                    } else {
-                        word |= kFarFlag;
-                        *reinterpret_cast<unsigned char*> (hdr + (size_t) pos * kHdrBytes + 4) = 1;
-                    }
+                    word |= kFarFlag;
+                    if (far_adj == nullptr) bad = 1;
                 }
             }
         }
         *hw = word;
+    }
+    __syncwarp();
+    /* second pass, after every row has its final word: HAS_FAR on the rows that produced the far operands
+       (several far rows, handled by different lanes, may name the same producer: atomic OR) */
+    for (int r = threadIdx.x & 31; r < rows; r += 32) {
+        const int word = *reinterpret_cast<const int*> (hdr + (size_t) r * kHdrBytes);
+        if ((word & (kFarFlag | kNopFlag | kParamFlag)) == kFarFlag)
+            atomicOr(reinterpret_cast<int*> (hdr + (size_t) (word & kIdMask) * kHdrBytes), kHasFarFlag);
     }
     __syncwarp();
     return __any_sync(0xffffffffu, bad);
@@ -523,8 +535,22 @@ __device__ __forceinline__ void tape_push2(ThreadTape* t, double dx0, int id0, d
     tape_push<UB>(t, dx1, id1, kEndFlag);
 }
 
-/* Close the operator whose slots were just pushed; returns its result id (the position of its END slot). */
+/* Close the operator whose slots were just pushed; returns its result id (the position of its END slot).
+   An operator that does not fit restarts the column at row 0 -- every later access stays inside this
+   thread's own column -- and says so: the uniform recorder hands the work-item to the general one, the
+   general one sets the sticky overflow bit (the sweep is skipped, the host reports the error). */
 __device__ __forceinline__ int tape_close_op(ThreadTape* t) {
+    if (t->next_id > t->cap_id) {
+        if (t->mode == kRecordUniform) {
+            t->bad = 1;
+            t->hdr_cur = t->hdr;
+            t->cell_off = kUnitCells * kCellRowBytes;
+        } else {
+            t->status |= kErrTapeOverflow;
+            t->cur = t->rows;
+        }
+        t->next_id = t->first_temp;
+    }
     t->nops++;
     return t->next_id - 1;
 }
@@ -541,11 +567,11 @@ __device__ __forceinline__ void tape_rewind(ThreadTape& t) {
 __device__ __forceinline__ void tape_read_row(const ThreadTape* t, int row, double* dx, int* word) {
     if (t->mode == kRecordUniform) {
         const int2 h = *reinterpret_cast<const int2*> (t->hdr + (size_t) row * kHdrBytes);
-        *word = h.x | ((h.y & 1) << 27);
-        *dx = *reinterpret_cast<const double*> (t->cells + ((unsigned) h.y & ~255u));
+        *word = h.x;
+        *dx = *reinterpret_cast<const double*> (t->cells + (unsigned) h.y);
     } else {
-        *word = *reinterpret_cast<const int*> (t->lane_words + (size_t) row * kLaneWordRowBytes);
-        *dx = *reinterpret_cast<const double*> (t->cells + (size_t) (row + kUnitCells) * kCellRowBytes);
+        *word = *reinterpret_cast<const int*> (t->rows + (size_t) row * kRowBytes + t->id_off);
+        *dx = *reinterpret_cast<const double*> (t->rows + (size_t) row * kRowBytes);
     }
 }
 
@@ -697,39 +723,31 @@ struct UniformSweep {
     double w;
     PendingParam& pend;
 
+    /* batch indices below 0 are clamped to batch 0: what is loaded for them is never used (the loop ends
+       before it would be), and the loads need no predicates */
     __device__ __forceinline__ void load_offsets(int b, unsigned (&a)[4]) const {
-        if (b >= 0) {
-            const char* p = hdr + (size_t) b * (4 * kHdrBytes);
-            const int4 x = ld_hdr2(p), y = ld_hdr2(p + 16);
-            a[0] = (unsigned) x.y & ~255u; a[1] = (unsigned) x.w & ~255u;
-            a[2] = (unsigned) y.y & ~255u; a[3] = (unsigned) y.w & ~255u;
-        } else {
-            a[0] = a[1] = a[2] = a[3] = 0u;
-        }
+        const char* p = hdr + (size_t) (b < 0 ? 0 : b) * (4 * kHdrBytes);
+        const int4 x = ld_hdr2(p), y = ld_hdr2(p + 16);
+        a[0] = (unsigned) x.y; a[1] = (unsigned) x.w; a[2] = (unsigned) y.y; a[3] = (unsigned) y.w;
     }
     __device__ __forceinline__ void load_words(int b, int (&wd)[4]) const {
-        if (b >= 0) {
-            const char* p = hdr + (size_t) b * (4 * kHdrBytes);
-            const int4 x = ld_hdr2(p), y = ld_hdr2(p + 16);
-            /* HAS_FAR travels in the low byte of the cell offset (tape_push): fold it into the id word */
-            wd[0] = x.x | ((x.y & 1) << 27); wd[1] = x.z | ((x.w & 1) << 27);
-            wd[2] = y.x | ((y.y & 1) << 27); wd[3] = y.z | ((y.w & 1) << 27);
-        } else {
-            wd[0] = wd[1] = wd[2] = wd[3] = kNopFlag;
-        }
+        const char* p = hdr + (size_t) (b < 0 ? 0 : b) * (4 * kHdrBytes);
+        const int4 x = ld_hdr2(p), y = ld_hdr2(p + 16);
+        wd[0] = x.x; wd[1] = x.z; wd[2] = y.x; wd[3] = y.z;
     }
     __device__ __forceinline__ void load_cells(const unsigned (&a)[4], double (&d)[4]) const {
 #pragma unroll
         for (int j = 0; j < 4; j++) d[j] = *reinterpret_cast<const double*> (cells + a[j]);
     }
+    /* One row.  FAR = false is the body of a batch none of whose four rows is FAR or HAS_FAR: no far code
+       at all (one test per BATCH decides).  Every test is on a warp-uniform value. */
+    template <bool FAR>
     __device__ __forceinline__ void row(int word, double dx, unsigned pop_addr, int me) {
         if (word < 0) { /* END: pop the adjoint of the operator that ends at this slot */
             w = lds_f64(pop_addr);
             sts_f64(pop_addr, 0.0);
         }
-        /* the two far cases share ONE test and live out of line: a call on the ~10 % of rows that need it
-           instead of a dozen predicated-off instructions on every row */
-        if (word & (kFarFlag | kHasFarFlag)) w = sweep_far_row(far_adj, word, me, w, dx);
+        if (FAR && (word & (kFarFlag | kHasFarFlag))) w = sweep_far_row(far_adj, word, me, w, dx);
         /* explicit rounding: the product is never contracted into one of the additions below, so the uniform
            and the general sweep (and every build) perform the same roundings per lane */
         const double c = __dmul_rn(w, dx);
@@ -751,8 +769,13 @@ struct UniformSweep {
         }
     }
     __device__ __forceinline__ void batch(int b, unsigned rb, const int (&wd)[4], const double (&d)[4]) {
+        if ((wd[0] | wd[1] | wd[2] | wd[3]) & (kFarFlag | kHasFarFlag)) {
 #pragma unroll
-        for (int j = 3; j >= 0; j--) row(wd[j], d[j], rb + 8u * j, 4 * b + j);
+            for (int j = 3; j >= 0; j--) row<true>(wd[j], d[j], rb + 8u * j, 4 * b + j);
+        } else {
+#pragma unroll
+            for (int j = 3; j >= 0; j--) row<false>(wd[j], d[j], rb + 8u * j, 4 * b + j);
+        }
     }
 };
 
@@ -770,7 +793,11 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, do
        parameters in the constant bank at every use) */
     unsigned wmask8 = (unsigned) t.wm1 << 3;
     asm volatile("" : "+r"(wmask8));
-    UniformSweep<MODE> S{t.hdr, t.cells, t.far_adj, T, wmask8, 0.0, pend};
+    /* likewise the two plane pointers (otherwise re-derived from the launch parameters every batch) */
+    const char* hdr = t.hdr;
+    const char* cells = t.cells;
+    asm volatile("" : "+l"(hdr), "+l"(cells));
+    UniformSweep<MODE> S{hdr, cells, t.far_adj, T, wmask8, 0.0, pend};
 
     int b = nb - 1;
     /* shared-memory offset of the ring entry of row 4b (W >= 4 and batches are aligned: the four pops of
@@ -801,16 +828,41 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, do
     }
 }
 
+/* The far cases of one row of the general sweep (per lane), out of line. */
+static __device__ __noinline__ double sweep_far_lane(char* far_adj, int idw, int me, double w, double dx) {
+    if ((idw & kHasFarFlag) && idw < 0) { /* contributions that came through the far plane */
+        double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
+        w = __dadd_rn(w, *fa);
+        *fa = 0.0;
+    }
+    if ((idw & kFarFlag) && !(idw & kNopFlag) && far_adj != nullptr) {
+        double* fa = reinterpret_cast<double*> (far_adj + (size_t) (idw & kIdMask) * kFarRowBytes);
+        *fa = __dadd_rn(*fa, __dmul_rn(w, dx));
+    }
+    return w;
+}
+
+#ifndef AD4CL_PREFETCH_BATCHES
+#define AD4CL_PREFETCH_BATCHES 2
+#endif
+constexpr int kPrefetchBatches = AD4CL_PREFETCH_BATCHES; /* the L2 prefetch runs this many batches below the one being fetched */
+
 /*
- * General sweep: every lane walks its OWN rows (lanes of a diverged warp hold tapes of different
- * lengths, id words may differ between lanes).  Out of line and by value: the hot entry stays small.
- * Four rows per batch, fetched one batch ahead of their use.  All lanes of the warp iterate together
- * (the independents' contributions are reduced with warp votes).  Returns Status bits
- * (AD4CL_DEBUG_BOUNDS builds).
+ * General sweep (rows of the general recorder): every lane walks its OWN rows -- lanes of a diverged warp
+ * hold tapes of different lengths, id words may differ between lanes.  Restates ad4cl.h:786-797 on the slot
+ * stream.  Four rows per batch, fetched one batch ahead of their use; `prefetch` additionally pulls the batch
+ * after the next into L2 (lanes 0-11 touch its 12 cache lines).  All lanes of the warp iterate together.
+ *
+ * Per batch ONE pair of 64-bit votes asks whether the four id words are the same in all 32 lanes (they are,
+ * whenever neighbouring work-items record the same operator sequence).  If so the rows are classified on
+ * warp-uniform branches and an independent's contribution is reduced over the warp without the ballot /
+ * leader loop, two contributions per butterfly (param_add_paired); if not, every lane classifies its own
+ * word.  Per lane both bodies perform the same fp64 operations in the same order.
+ * Out of line and by value: the hot entry stays small.  Returns Status bits (AD4CL_DEBUG_BOUNDS builds).
  */
 template <int MODE>
-static __device__ __noinline__ int tape_sweep_general(const char* cells, const char* lane_words,
-        char* far_adj, int rows, int first_temp, int wmask, int out_id, double seed, SweepTarget T, int cap_rows) {
+static __device__ __noinline__ int tape_sweep_general(const char* rows_base, int id_off, char* far_adj, int rows,
+        int first_temp, int wmask, int out_id, double seed, SweepTarget T, int cap_rows, int prefetch) {
     constexpr int U = kSweepUnroll;
     rows = sweep_seed<MODE>(rows, first_temp, wmask, out_id, seed, T);
     int status = kOk;
@@ -820,7 +872,9 @@ static __device__ __noinline__ int tape_sweep_general(const char* cells, const c
         rows = 0;
     }
 #endif
+    PendingParam pend = {0.0, -1};   /* flushed before returning: the caller's pending pair is its own */
     const unsigned pad_off = (unsigned) (wmask + 1) << 3;
+    const char* cur = rows_base + (size_t) rows * kRowBytes;
     double w = 0.0;
     double dx_now[U], dx_next[U];
     int id_now[U], id_next[U];
@@ -829,82 +883,126 @@ static __device__ __noinline__ int tape_sweep_general(const char* cells, const c
 #pragma unroll
     for (int j = 0; j < U; j++) {
         if (j < head) {
-            const int r = rows - 1 - j;
-            dx_now[j] = *reinterpret_cast<const double*> (cells + (size_t) (r + kUnitCells) * kCellRowBytes);
-            id_now[j] = *reinterpret_cast<const int*> (lane_words + (size_t) r * kLaneWordRowBytes);
+            const char* row = cur - (j + 1) * kRowBytes;
+            dx_now[j] = *reinterpret_cast<const double*> (row);
+            id_now[j] = *reinterpret_cast<const int*> (row + id_off);
         } else {
             dx_now[j] = 0.0;
             id_now[j] = kNopFlag;
         }
     }
-    int top = rows;                 /* slot j of the current batch has index top - 1 - j */
-    int next_top = rows - head;
+    cur -= (size_t) head * kRowBytes;
+    int idx = rows;            /* slot j of the batch in flight has index idx - 1 - j */
+    int next_idx = rows - head;
+    int batches = rows / U;    /* whole batches still in memory */
     bool more = true;
     while (__any_sync(0xffffffffu, more)) {
-        const bool fetch = next_top > 0;
+        const bool fetch = batches > 0;
+        if (fetch) {
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            if (fetch) {
-                const int r = next_top - 1 - j;
-                dx_next[j] = *reinterpret_cast<const double*> (cells + (size_t) (r + kUnitCells) * kCellRowBytes);
-                id_next[j] = *reinterpret_cast<const int*> (lane_words + (size_t) r * kLaneWordRowBytes);
-            } else {
+            for (int j = 0; j < U; j++) {
+                const char* row = cur - (j + 1) * kRowBytes;
+                dx_next[j] = *reinterpret_cast<const double*> (row);
+                id_next[j] = *reinterpret_cast<const int*> (row + id_off);
+            }
+            cur -= U * kRowBytes;
+            --batches;
+            if (prefetch && batches >= kPrefetchBatches && id_off > kRowIdOffset - 4 * 3 * U) {
+                const int lane = (kRowIdOffset - id_off) >> 2;
+                const char* line = cur - lane * 8 - kPrefetchBatches * U * kRowBytes + lane * 128;
+                asm volatile("prefetch.L2 [%0];" : : "l"(line));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; j++) {
                 dx_next[j] = 0.0;
                 id_next[j] = kNopFlag;
             }
         }
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            int idw = id_now[j];
-            const int me = top - 1 - j;
 #if AD4CL_DEBUG_BOUNDS
-            {   /* operands precede their use; independents are below first_temp; far rows need the plane */
-                const int cl = idw & (kNopFlag | kParamFlag), pl = idw & kIdMask;
-                bool bad = (cl == 0 && (pl < 0 || pl >= me)) || (cl == kParamFlag && pl >= first_temp);
-                if ((idw & (kFarFlag | kHasFarFlag)) && (far_adj == nullptr || me < 0 || me >= cap_rows)) bad = true;
-                if (bad) {
-                    status |= kErrBounds;
-                    idw = kNopFlag;
-                }
+#pragma unroll
+        for (int j = 0; j < U; j++) {   /* operands precede their use; independents are below first_temp; far rows need the plane */
+            const int idw = id_now[j], me = idx - 1 - j;
+            const int cl = idw & (kNopFlag | kParamFlag), pl = idw & kIdMask;
+            bool bad = (cl == 0 && (pl < 0 || pl >= me)) || (cl == kParamFlag && pl >= first_temp);
+            if ((idw & (kFarFlag | kHasFarFlag)) && (far_adj == nullptr || me < 0 || me >= cap_rows)) bad = true;
+            if (bad) {
+                status |= kErrBounds;
+                id_now[j] = kNopFlag;
             }
+        }
 #endif
-            if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
-                const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
-                w = lds_f64(r);
-                sts_f64(r, 0.0);
-            }
-            if (idw & (kFarFlag | kHasFarFlag)) { /* rare: ONE test for both far cases */
-                if ((idw & kHasFarFlag) && idw < 0) { /* contributions that came through the far plane */
-                    double* fa = reinterpret_cast<double*> (far_adj + (size_t) me * kFarRowBytes);
-                    w = __dadd_rn(w, *fa);
-                    *fa = 0.0;
+        int same01 = 0, same23 = 0;
+#if AD4CL_LANE_UNIFORM_BATCHES
+        __match_all_sync(0xffffffffu, ((unsigned long long) (unsigned) id_now[1] << 32) | (unsigned) id_now[0], &same01);
+        __match_all_sync(0xffffffffu, ((unsigned long long) (unsigned) id_now[3] << 32) | (unsigned) id_now[2], &same23);
+#endif
+        if (same01 && same23) {
+            /* ---- warp-uniform batch: every test below is on a value all 32 lanes share ---- */
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int idw = id_now[j];
+                const int me = idx - 1 - j;
+                if (idw < 0) { /* END: pop the adjoint of the operator that ends at this slot */
+                    const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
+                    w = lds_f64(r);
+                    sts_f64(r, 0.0);
                 }
-                if ((idw & kFarFlag) && !(idw & kNopFlag) && far_adj != nullptr) {
-                    double* fa = reinterpret_cast<double*> (far_adj + (size_t) (idw & kIdMask) * kFarRowBytes);
-                    *fa = __dadd_rn(*fa, __dmul_rn(w, dx_now[j]));
+                if (idw & (kFarFlag | kHasFarFlag)) w = sweep_far_lane(far_adj, idw, me, w, dx_now[j]);
+                const double c = __dmul_rn(w, dx_now[j]);
+                if ((idw & (kNopFlag | kParamFlag | kFarFlag)) == 0) {
+                    const unsigned a = T.ring + ((unsigned) (idw & wmask) << 3);
+                    sts_f64(a, __dadd_rn(lds_f64(a), c));
+                }
+                if ((idw & (kNopFlag | kParamFlag)) == kParamFlag) {
+                    const int id = idw & kIdMask;
+                    if (MODE == kAccThread) {
+                        const unsigned a = T.thread_acc + (unsigned) id * T.stride;
+                        sts_f64(a, __dadd_rn(lds_f64(a), c));
+                    } else if (MODE == kAccWarp) {
+                        param_add_paired(T.warp_acc, pend, id, c);
+                    } else {
+                        const double v = warp_sum(c);
+                        if (id_off == kRowIdOffset) atomicAdd(&T.global_acc[id], v);   /* lane 0 */
+                    }
                 }
             }
-            const int payload = idw & kIdMask;
-            const double c = __dmul_rn(w, dx_now[j]);
-            const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
-            {   /* Branch-free scatter: a recent temporary adds to its ring entry, with per-thread
-                   accumulators (kAccThread) an independent adds to its accumulator, and a slot of any
-                   other class adds to the pad entry of this thread's ring (index W), which nothing reads. */
-                unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
-                if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
-                sts_f64(a, __dadd_rn(lds_f64(a), c));
+        } else {
+            /* ---- every lane classifies its own word ---- */
+            if (MODE == kAccWarp) param_flush(T.warp_acc, pend);   /* keep the order of the additions fixed */
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int idw = id_now[j];
+                const int me = idx - 1 - j;
+                if (idw < 0) {
+                    const unsigned r = T.ring + ((unsigned) (me & wmask) << 3);
+                    w = lds_f64(r);
+                    sts_f64(r, 0.0);
+                }
+                if (idw & (kFarFlag | kHasFarFlag)) w = sweep_far_lane(far_adj, idw, me, w, dx_now[j]);
+                const int payload = idw & kIdMask;
+                const double c = __dmul_rn(w, dx_now[j]);
+                const int cls = idw & (kNopFlag | kParamFlag | kFarFlag);
+                {   /* Branch-free scatter: a recent temporary adds to its ring entry, with per-thread
+                       accumulators (kAccThread) an independent adds to its accumulator, and a slot of any
+                       other class adds to the pad entry of this thread's ring (index W), which nothing reads. */
+                    unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
+                    if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
+                    sts_f64(a, __dadd_rn(lds_f64(a), c));
+                }
+                if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
             }
-            if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {
             dx_now[j] = dx_next[j];
             id_now[j] = id_next[j];
         }
-        top = next_top;
-        next_top -= U;
+        idx = next_idx;
+        next_idx -= U;
         more = fetch;
     }
+    if (MODE == kAccWarp) param_flush(T.warp_acc, pend);
     (void) cap_rows;
     return status;
 }

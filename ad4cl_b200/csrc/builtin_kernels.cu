@@ -53,8 +53,10 @@ AD4CL_OBJECTIVE_ENTRY(matrix_elementwise,
     (struct ad_variable* A, struct ad_variable* B, int width, int op),
     (gs, gradient_stack, A, B, out, width, op))
 
-#define ROW(NAME, SIG) {#NAME, {(const void*) &AD4CL_ENTRY_NAME(NAME, 0), (const void*) &AD4CL_ENTRY_NAME(NAME, 1), \
-                             (const void*) &AD4CL_ENTRY_NAME(NAME, 2)}, SIG}
+#define ROW(NAME, SIG) {#NAME, {{(const void*) &AD4CL_ENTRY_NAME2(NAME, u, 0), (const void*) &AD4CL_ENTRY_NAME2(NAME, u, 1), \
+                              (const void*) &AD4CL_ENTRY_NAME2(NAME, u, 2)},                                       \
+                             {(const void*) &AD4CL_ENTRY_NAME2(NAME, m, 0), (const void*) &AD4CL_ENTRY_NAME2(NAME, m, 1), \
+                              (const void*) &AD4CL_ENTRY_NAME2(NAME, m, 2)}}, SIG}
 extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(linreg2_g, "GSVVDDOi"),
     ROW(linreg2_p, "GSVVDDOi"),
@@ -71,5 +73,5 @@ extern "C" const ad4cl_builtin_row AD4CL_BUILTIN_TABLE[] = {
     ROW(op_probe, "GSVDDOiii"),
     ROW(matrix_product, "GSVVOii"),
     ROW(matrix_elementwise, "GSVVOii"),
-    {nullptr, {nullptr, nullptr, nullptr}, nullptr},
+    {nullptr, {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}, nullptr},
 };

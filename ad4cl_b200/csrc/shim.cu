@@ -175,12 +175,14 @@ struct ad4cl_buffer {
 struct ad4cl_kernel {
     ad4cl_context* ctx = nullptr;
     std::string name, signature;
-    const void* entries[3] = {nullptr, nullptr, nullptr};  /* ahead-of-time kernel, per accumulator mode */
+    const void* entries[2][3] = {};  /* ahead-of-time kernel: [recorder 0 uniform / 1 lane][accumulator mode] */
     const void* entry = nullptr;   /* the one selected by prepare() */
     std::vector<const ad4cl_static_row*> static_rows; /* register-tier instances of this built-in kernel */
     bool use_static = false;       /* prepare() selected one of them */
     CUmodule module = nullptr;     /* NVRTC kernel */
-    CUfunction functions[3] = {nullptr, nullptr, nullptr};
+    CUfunction functions[2][3] = {};
+    int recorder = 1;              /* the recorder (kernel) in use: 0 uniform-first, 1 lane */
+    int acc = 0;                   /* the accumulator mode in use */
     CUfunction function = nullptr;
     std::vector<Arg> args;
     ad4cl_kernel_config cfg{};
@@ -211,6 +213,7 @@ struct ad4cl_kernel {
     /* the host evaluation path replayed as one CUDA graph: [0] objective only, [1] with gradient */
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     ad4cl_comm* graph_comm = nullptr;   /* the communicator the captured graphs were built with */
+    bool tune_pending = false;          /* AD4CL_RECORDER_AUTO / AD4CL_PREFETCH_AUTO not decided yet */
     bool graph_disabled = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ad4cl_eval_stats stats{};
@@ -314,8 +317,11 @@ int prepare(ad4cl_kernel* k, int nparams) {
 
     int acc = c.acc_mode;
     if (acc == AD4CL_ACC_AUTO) acc = nparams <= 16 ? AD4CL_ACC_THREAD : (nparams <= 512 ? AD4CL_ACC_WARP : AD4CL_ACC_GLOBAL);
-    if (k->module) k->function = k->functions[acc];
-    else k->entry = k->entries[acc];
+    k->acc = acc;
+    k->recorder = c.recorder == AD4CL_RECORDER_UNIFORM ? 0 : 1;   /* AUTO starts with the lane kernel until tuned */
+    if (k->module && k->functions[0][acc] == nullptr) k->recorder = 1;   /* a kernel with work-group barriers has no uniform build */
+    if (k->module) k->function = k->functions[k->recorder][acc];
+    else k->entry = k->entries[k->recorder][acc];
     const int max_ops = std::max(c.max_ops, 1);
     const unsigned cap_slots = (unsigned) (c.max_slots > 0 ? c.max_slots : 2 * max_ops);
     const bool far = c.far_plane != 0;
@@ -377,6 +383,21 @@ int prepare(ad4cl_kernel* k, int nparams) {
     int per_sm = 0;
     int rc = occupancy(k, block, smem, &per_sm);
     if (rc != AD4CL_OK) return rc;
+    if (!srow) { /* the other recorder's kernel may be launched too (AUTO times both): same opt-in, the smaller occupancy */
+        const int other = 1 - k->recorder;
+        if (k->module ? k->functions[other][acc] != nullptr : k->entries[other][acc] != nullptr) {
+            const void* e0 = k->entry;
+            CUfunction f0 = k->function;
+            if (k->module) k->function = k->functions[other][acc];
+            else k->entry = k->entries[other][acc];
+            int per_sm2 = 0;
+            rc = occupancy(k, block, smem, &per_sm2);
+            k->entry = e0;
+            k->function = f0;
+            if (rc != AD4CL_OK) return rc;
+            per_sm = std::min(per_sm, per_sm2);
+        }
+    }
     if (per_sm < 1) return fail(AD4CL_ERR_INVALID, "kernel %s does not fit on an SM (block %d, smem %zu)", k->name.c_str(), block, smem);
     if (c.blocks_per_sm > 0) per_sm = std::min(per_sm, c.blocks_per_sm);
     const long long ngroups = (g0 / l0) * (g1 / l1);
@@ -424,7 +445,11 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.window = window;
     L.use_far = far ? 1 : 0;
     L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
-    k->stats.sweep_prefetch = 0; /* round 2: the compact tape stays L2 resident where the prefetch used to pay; the option is accepted and ignored */
+    L.sweep_prefetch = c.sweep_prefetch == AD4CL_PREFETCH_ON ? 1 : 0;
+    /* AUTO: decided by autotune_recorder on the first gradient evaluation (the register tier has no choice to make) */
+    k->tune_pending = !srow && (c.recorder == AD4CL_RECORDER_AUTO || c.sweep_prefetch == AD4CL_PREFETCH_AUTO);
+    k->stats.recorder = k->tune_pending && c.recorder == AD4CL_RECORDER_AUTO ? -1 : (srow ? -1 : k->recorder);
+    k->stats.sweep_prefetch = k->tune_pending && c.sweep_prefetch == AD4CL_PREFETCH_AUTO ? -1 : L.sweep_prefetch;
     L.cap_slots = cap_slots;
     L.arena = k->arena;
     L.warp_region = region;
@@ -593,6 +618,67 @@ int enqueue(ad4cl_kernel* k, const double* theta_dev, double* result_dev, int wa
     return AD4CL_OK;
 }
 
+/*
+ * AD4CL_RECORDER_AUTO / AD4CL_PREFETCH_AUTO: time one evaluation (CUDA events on the context's stream) for
+ * each admissible combination of recorder and sweep prefetch and keep the fastest for this configuration.
+ * Runs once, on the first gradient evaluation, never inside a stream capture (a sharded evaluation tunes
+ * with local evaluations: the peers take no part).  The first run also warms up; a combination that takes
+ * longer than 200 ms is not run a second time.  The choice changes no result beyond the order in which an
+ * independent's contributions are summed over a warp.
+ */
+int autotune_recorder(ad4cl_kernel* k, const double* theta_dev) {
+    cudaStream_t st = k->ctx->stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return AD4CL_OK; /* a caller-owned stream under graph capture cannot be timed: decide on a later call */
+    }
+    k->tune_pending = false;
+    struct Cand { int recorder, prefetch; float ms; };
+    std::vector<Cand> cands;
+    const ad4cl_kernel_config& c = k->cfg;
+    for (int rec = 0; rec < 2; rec++) {
+        if (c.recorder != AD4CL_RECORDER_AUTO && (c.recorder == AD4CL_RECORDER_LANE) != (rec == 1)) continue;
+        if (rec == 0 && k->module && k->functions[0][k->acc] == nullptr) continue;
+        for (int pf = 0; pf < 2; pf++) {
+            if (rec == 0 && pf == 1) continue; /* the uniform sweep has no prefetch */
+            if (rec == 1 && c.sweep_prefetch != AD4CL_PREFETCH_AUTO && (c.sweep_prefetch == AD4CL_PREFETCH_ON) != (pf == 1)) continue;
+            if (k->L.tape_in_smem && pf == 1) continue;
+            cands.push_back({rec, pf, 1e30f});
+        }
+    }
+    if (cands.size() > 1) {
+        for (int round = 0; round < 2; round++) {
+            for (Cand& cd : cands) {
+                if (round == 1 && cd.ms > 200.f && cd.ms < 1e29f) continue;
+                k->recorder = cd.recorder;
+                if (k->module) k->function = k->functions[k->recorder][k->acc];
+                else k->entry = k->entries[k->recorder][k->acc];
+                k->L.sweep_prefetch = cd.prefetch;
+                CUDA_TRY(cudaEventRecord(k->ev0, st));
+                int rc = enqueue(k, theta_dev, k->result_dev, 1, 0);
+                if (rc != AD4CL_OK) return rc;
+                CUDA_TRY(cudaEventRecord(k->ev1, st));
+                CUDA_TRY(cudaEventSynchronize(k->ev1));
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, k->ev0, k->ev1));
+                if (round == 1 || ms > 200.f) cd.ms = std::min(cd.ms, ms);
+            }
+        }
+    }
+    const Cand* best = &cands[0];
+    for (const Cand& cd : cands)
+        if (cd.ms < best->ms) best = &cd;
+    k->recorder = best->recorder;
+    if (k->module) k->function = k->functions[k->recorder][k->acc];
+    else k->entry = k->entries[k->recorder][k->acc];
+    k->L.sweep_prefetch = best->prefetch;
+    k->stats.recorder = k->recorder;
+    k->stats.sweep_prefetch = k->L.sweep_prefetch;
+    CUDA_TRY(cudaMemsetAsync(k->status_dev, 0, sizeof (int), st)); /* an error shows up again in the evaluation proper */
+    return AD4CL_OK;
+}
+
 int status_to_error(ad4cl_kernel* k, int st) {
     if (st == 0) return AD4CL_OK;
     /* leave the arena clean for the next evaluation (far bitmaps may be dirty) */
@@ -755,7 +841,8 @@ int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int referenc
     for (const ad4cl_builtin_row* r = tab; r->name; r++) {
         if (strcmp(r->name, name) == 0) {
             ad4cl_kernel* k = new_kernel(ctx, name, r->signature);
-            for (int m = 0; m < 3; m++) k->entries[m] = r->entry[m];
+            for (int rc2 = 0; rc2 < 2; rc2++)
+                for (int m = 0; m < 3; m++) k->entries[rc2][m] = r->entry[rc2][m];
             const ad4cl_static_row* const stabs[2][2] = {{ad4cl_static_table_fixed_p2, ad4cl_static_table_fixed_p10},
                 {ad4cl_static_table_quirks_p2, ad4cl_static_table_quirks_p10}};
             for (const ad4cl_static_row* st : stabs[reference_quirks ? 1 : 0])
@@ -867,13 +954,17 @@ int ad4cl_cuda_kernel_from_cubin(ad4cl_context* ctx, const void* cubin, size_t c
         delete k;
         return fail(AD4CL_ERR_CUDA, "cuModuleLoadData failed: %d", (int) r);
     }
-    for (int m = 0; m < 3; m++) {
-        std::string fn = std::string(entry) + "__entry_m" + std::to_string(m);
-        r = driver().cuModuleGetFunction(&k->functions[m], k->module, fn.c_str());
-        if (r != CUDA_SUCCESS) {
-            driver().cuModuleUnload(k->module);
-            delete k;
-            return fail(AD4CL_ERR_CUDA, "cuModuleGetFunction(%s) failed: %d", fn.c_str(), (int) r);
+    for (int rec = 0; rec < 2; rec++) {
+        for (int m = 0; m < 3; m++) {
+            std::string fn = std::string(entry) + (rec == 0 ? "__entry_u" : "__entry_m") + std::to_string(m);
+            r = driver().cuModuleGetFunction(&k->functions[rec][m], k->module, fn.c_str());
+            if (r != CUDA_SUCCESS) {
+                k->functions[rec][m] = nullptr;
+                if (rec == 0) continue; /* no uniform build: a kernel with work-group barriers */
+                driver().cuModuleUnload(k->module);
+                delete k;
+                return fail(AD4CL_ERR_CUDA, "cuModuleGetFunction(%s) failed: %d", fn.c_str(), (int) r);
+            }
         }
     }
     k->cfg.reference_quirks = reference_quirks;
@@ -970,6 +1061,7 @@ int ad4cl_cuda_kernel_config_default(ad4cl_kernel_config* cfg) {
     cfg->tape_tier = AD4CL_TAPE_AUTO;
     cfg->epilogue = AD4CL_EPILOGUE_SUM;
     cfg->sweep_prefetch = AD4CL_PREFETCH_AUTO;
+    cfg->recorder = AD4CL_RECORDER_AUTO;
     return AD4CL_OK;
 }
 
@@ -991,6 +1083,10 @@ int ad4cl_cuda_eval_device(ad4cl_kernel* k, const double* theta_dev, int nparams
     CUDA_TRY(cudaSetDevice(k->ctx->device));
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
+    if (k->tune_pending && want_gradient) {
+        rc = autotune_recorder(k, theta_dev);
+        if (rc != AD4CL_OK) return rc;
+    }
     return enqueue(k, theta_dev, result_dev, want_gradient, apply_epilogue);
 }
 
@@ -1018,6 +1114,10 @@ int ad4cl_cuda_eval_device_sharded(ad4cl_kernel* k, ad4cl_comm* comm, const doub
     CUDA_TRY(cudaSetDevice(k->ctx->device));
     int rc = prepare(k, nparams);
     if (rc != AD4CL_OK) return rc;
+    if (k->tune_pending && want_gradient) { /* local evaluations only: the peers take no part */
+        rc = autotune_recorder(k, theta_dev);
+        if (rc != AD4CL_OK) return rc;
+    }
     return enqueue(k, theta_dev, result_dev, want_gradient, 1, nullptr, comm);
 }
 
@@ -1050,6 +1150,13 @@ static int eval_host(ad4cl_kernel* k, ad4cl_comm* comm, const double* theta, int
     cudaStream_t st = k->ctx->stream;
     const int want = grad != nullptr ? 1 : 0;
     if (nparams > 0) memcpy(k->theta_pinned, theta, sizeof (double) * (size_t) nparams);
+    if (k->tune_pending && want) { /* local evaluations only: the peers of a sharded call take no part */
+        if (nparams > 0)
+            CUDA_TRY(cudaMemcpyAsync(k->theta_dev, k->theta_pinned, sizeof (double) * (size_t) nparams, cudaMemcpyHostToDevice, st));
+        rc = autotune_recorder(k, k->theta_dev);
+        if (rc != AD4CL_OK) return rc;
+        k->drop_graphs();
+    }
     /* Replay the whole evaluation as one CUDA graph (captured on first use; the launch's
        arguments are fixed until an argument, the configuration or the communicator changes; the
        all-reduce epoch lives in device memory).  Profiling needs events around the kernel, so it
@@ -1413,12 +1520,13 @@ int ad4cl_cuda_export_tape(ad4cl_kernel* k, const double* theta, int nparams, in
         HostEntry cur{};
         int have = 0;
         for (int s = 0; s < nslots; s++) {
-            /* the export launch records with the general recorder: row s = this lane's id word in the
-               lane-word plane and its partial in cell s + 2 (ad4cl_tape.cuh) */
+            /* the export launch records with the general recorder: row s = 384 bytes, the 32 lanes' partials
+               then their id words, after the two constant cells of the cell plane (ad4cl_tape.cuh) */
+            const char* row = col + lay.off_cells + (size_t) ad4cl::kUnitCells * ad4cl::kCellRowBytes + (size_t) s * ad4cl::kRowBytes;
             int word;
-            memcpy(&word, col + lay.off_lane_words + (size_t) s * ad4cl::kLaneWordRowBytes + lane * 4, 4);
+            memcpy(&word, row + ad4cl::kRowIdOffset + lane * 4, 4);
             double dx;
-            memcpy(&dx, col + lay.off_cells + (size_t) (s + ad4cl::kUnitCells) * ad4cl::kCellRowBytes + lane * 8, 8);
+            memcpy(&dx, row + lane * 8, 8);
             if (!(word & ad4cl::kNopFlag)) {
                 const int payload = word & ad4cl::kIdMask;
                 const int id = (word & ad4cl::kParamFlag) ? payload : base + op_of_slot[(size_t) payload];

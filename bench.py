@@ -435,6 +435,8 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--prefetch", default="auto", choices=["auto", "off", "on"],
                     help="sweep L2 prefetch (auto: the library times both on the first evaluation)")
+    ap.add_argument("--recorder", default="auto", choices=["auto", "uniform", "lane"],
+                    help="tape recorder (auto: the library times uniform / lane / lane + prefetch on the first evaluation)")
     ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
                     help="N > 1: the library's one-shot NVLink all-reduce (default) or torch.distributed NCCL")
     args = ap.parse_args()
@@ -501,6 +503,8 @@ def main():
         cfg["blocks_per_sm"] = args.blocks_per_sm
     if args.prefetch != "auto":
         cfg["prefetch"] = args.prefetch
+    if args.recorder != "auto":
+        cfg["recorder"] = args.recorder
     k = W.bind(ctx, w, **cfg)
 
     theta_host = torch.from_numpy(np.ascontiguousarray(w.theta)).pin_memory()
@@ -667,7 +671,9 @@ def main():
             "launch": dict(ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
                            l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
-                           tape_tier=stats["tape_tier"], acc_mode=args.acc, launches_per_eval=k.launches_per_eval),
+                           tape_tier=stats["tape_tier"], acc_mode=args.acc, launches_per_eval=k.launches_per_eval,
+                           recorder=stats["recorder"], sweep_prefetch=stats["sweep_prefetch"],
+                           recorder_choice="auto-tuned on the first evaluation" if args.recorder == "auto" else "forced"),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     # ad4cl_cuda_eval / ad4cl_cuda_eval_sharded: P doubles up, [grad, f, ops, slots, status] down,
                     # replayed as one CUDA graph (H2D, ONE kernel, D2H)

@@ -77,13 +77,26 @@ enum {
                                an instance exists and was fully scalarised, else AD4CL_TAPE_HBM. */
 };
 
-/* Round 1: L2 prefetch of tape rows in the sweep, auto-tuned.  Since round 2 the tape of a warp is a
-   warp-uniform header stream plus per-lane cells (ad4cl_tape.cuh): short tapes stay L2 resident and
-   long ones stream at the HBM rate, so the option is accepted for compatibility and ignored. */
+/* L2 prefetch of tape rows two batches ahead in the sweep of the LANE recorder.  Helps a latency-bound
+   evaluation, costs a bandwidth-bound one a few percent; results are bit-identical either way. */
 enum {
     AD4CL_PREFETCH_AUTO = -1,
     AD4CL_PREFETCH_OFF = 0,
     AD4CL_PREFETCH_ON = 1
+};
+
+/* How a work-item's tape is recorded in the arena / shared-memory tiers (ad4cl_tape.cuh):
+     UNIFORM  optimistic: ONE 8-byte header per warp and slot + an 8-byte cell per lane only for partials that
+              are not +1/-1 (a third of the bytes; short tapes never leave L2); a warp whose lanes turn out to
+              record different tapes re-records the work-item with the LANE recorder.
+     LANE     the round-1 stream, 12 bytes per lane and slot; its sweep detects warp-uniform batches itself.
+     AUTO     times UNIFORM, LANE and LANE + prefetch on the first gradient evaluation of a configured kernel
+              (six extra evaluations, once) and keeps the fastest.  Never changes a result beyond the order in
+              which an independent's contributions are summed over a warp (bit-identical with <= 16 independents). */
+enum {
+    AD4CL_RECORDER_AUTO = -1,
+    AD4CL_RECORDER_UNIFORM = 0,
+    AD4CL_RECORDER_LANE = 1
 };
 
 /* scalar epilogue applied to S = sum_i out_i */
@@ -105,7 +118,8 @@ typedef struct ad4cl_kernel_config {
     double epilogue_n;         /* n of the epilogue; 0 = number of data work-items */
     int blocks_per_sm;         /* persistent grid = SMs x this; 0 = occupancy maximum */
     int reference_quirks;      /* builtin kernels only: 1 = reference arithmetic as written */
-    int sweep_prefetch;        /* AD4CL_PREFETCH_*: accepted and ignored since round 2 */
+    int sweep_prefetch;        /* AD4CL_PREFETCH_* */
+    int recorder;              /* AD4CL_RECORDER_* */
 } ad4cl_kernel_config;
 
 typedef struct ad4cl_eval_stats {
@@ -115,8 +129,9 @@ typedef struct ad4cl_eval_stats {
     size_t smem_bytes;
     size_t arena_bytes;
     float kernel_ms;        /* device time of the last evaluation (both launches) */
-    int sweep_prefetch;     /* always 0 since round 2 */
+    int sweep_prefetch;     /* the setting in use: 0 off, 1 on, -1 not decided yet (AUTO before the first gradient evaluation) */
     int tape_tier;          /* the AD4CL_TAPE_* tier in use (what AUTO resolved to) */
+    int recorder;           /* the AD4CL_RECORDER_* in use, -1 not decided yet */
 } ad4cl_eval_stats;
 
 int ad4cl_cuda_init(int device, ad4cl_context** ctx);

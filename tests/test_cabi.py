@@ -89,6 +89,7 @@ def test_config_defaults():
     cfg = host.KernelConfig()
     assert host.lib.ad4cl_cuda_kernel_config_default(ctypes.byref(cfg)) == 0
     assert (cfg.acc_mode, cfg.tape_tier, cfg.sweep_prefetch) == (host.ACC["auto"], host.TAPE["auto"], host.PREFETCH["auto"])
+    assert cfg.recorder == host.RECORDER["auto"]
     assert cfg.far_plane == 1 and cfg.global_size[1] == 1 and cfg.max_ops > 0
     assert host.lib.ad4cl_cuda_kernel_config_default(None) != 0
     assert b"NULL" in host.lib.ad4cl_cuda_last_error()

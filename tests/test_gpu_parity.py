@@ -122,21 +122,34 @@ def test_objective_only(ctx, oracle_api):
 @pytest.mark.parametrize("name,n,kw", [("catch_at_age", 200000, {}), ("tape_stress", 20000, {"steps": 200}),
                                         ("regression_linear", 50001, {})],
                          ids=["catch_at_age", "tape_stress", "regression_linear"])
-def test_replay_and_ignored_prefetch_option_never_change_a_bit(ctx, name, n, kw):
-    """The captured-graph replay returns the bits of the first evaluation, and the round-1 prefetch option
-    (accepted for compatibility, ignored since the round-2 tape format) cannot change anything."""
+def test_recorder_and_prefetch_choices_do_not_change_the_result(ctx, name, n, kw):
+    """AD4CL_RECORDER_* x AD4CL_PREFETCH_* (include/ad4cl_cuda.h) are performance choices: the captured-graph
+    replay returns the bits of the first evaluation; the sweep prefetch never changes a bit; the two recorders
+    agree bit for bit with per-thread accumulators (P <= 16) and to 1e-13 with per-warp ones (only the order in
+    which an independent's contributions are summed over a warp differs); AUTO settles on one of them."""
     w = W.describe(name, n, **kw)
     out = {}
-    for mode in ("off", "on", "auto"):
-        k = W.bind(ctx, w, prefetch=mode)
+    for rec, pf in (("lane", "off"), ("lane", "on"), ("uniform", "off"), ("auto", "auto")):
+        k = W.bind(ctx, w, recorder=rec, prefetch=pf, tape="hbm")
         try:
+            if rec == "auto":
+                assert k.eval(w.theta, want_grad=False)[1] is None
+                assert k.stats()["recorder"] == "n/a"            # objective-only evaluations record nothing: no decision yet
             f, g = k.eval(w.theta)
-            f2, g2 = k.eval(w.theta)                         # the captured-graph replay
+            f2, g2 = k.eval(w.theta)                             # the captured-graph replay
             assert f == f2 and np.array_equal(g, g2)
-            assert k.launches_per_eval == 1                  # pack + record + sweep + both reduction stages: ONE launch
-            out[mode] = (f, g, k.stats()["sweep_prefetch"])
+            assert k.launches_per_eval == 1                      # pack + record + sweep + both reduction stages: ONE launch
+            st = k.stats()
+            assert st["recorder"] in ("lane", "uniform") and st["sweep_prefetch"] in (0, 1)
+            out[(rec, pf)] = (f, g)
         finally:
             k.free()
-    for mode in ("on", "auto"):
-        assert out[mode][0] == out["off"][0]
-        assert np.array_equal(out[mode][1], out["off"][1])
+    base = out[("lane", "off")]
+    assert out[("lane", "on")][0] == base[0] and np.array_equal(out[("lane", "on")][1], base[1])
+    for key in (("uniform", "off"), ("auto", "auto")):
+        f, g = out[key]
+        if w.nparams <= 16:
+            assert f == base[0] and np.array_equal(g, base[1])
+        else:
+            assert abs(f - base[0]) <= 1e-13 * abs(base[0])
+            assert np.max(np.abs(g - base[1])) <= 1e-13 * np.max(np.abs(base[1]))
