@@ -71,6 +71,7 @@ struct LaunchInfo {
        into seeds s_i = dh/d out_i.  Pass 2 (seeds set): the sweep of work-item i starts from s_i instead of 1,
        so the reduced gradient is sum_i s_i * d out_i / d theta.  Both indexed like the kernel's own out[]. */
     int sweep_prefetch;     /* general sweep: L2 prefetch two batches ahead */
+    int lockstep;           /* the warps of a work-group wait for each other before every work-item */
     const double* seeds;
     double* out_values;
     long long n_user;       /* work-items the caller configured (the NDRange is padded to whole work-groups) */
@@ -83,8 +84,11 @@ struct ItemIds {
     int gid0, gid1;
 };
 
+#ifndef AD4CL_STATIC_MAX_BLOCK
+#define AD4CL_STATIC_MAX_BLOCK 256   /* register tier: the scalarised tape wants the registers of a 256-thread block */
+#endif
 #ifndef AD4CL_MAX_BLOCK
-#define AD4CL_MAX_BLOCK 256
+#define AD4CL_MAX_BLOCK 768
 #endif
 /* 1: the user kernel synchronises its work-group (barrier()): it cannot be re-run by a single warp, so
    the entry is built with the general recorder only (the shim defines this for JIT kernels whose text
@@ -420,6 +424,10 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     const int groups0 = L.g0 / L.l0;           /* work-groups along dimension 0 */
     const int l1 = B / L.l0;
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        /* lock step: keep the warps of a CTA inside the same work-item's code -- 3 (or 1) fetch streams
+           per SM instead of 24; the hot code of a long objective is larger than the 32 KB L1.5 instruction
+           cache and the warps otherwise starve on instruction fetch (profiles/README.md) */
+        if (L.lockstep) __syncthreads();
         /* NDRange coordinates of this thread's work-item in work-group `grp` */
         const int grp0 = (int) (grp % groups0), grp1 = (int) (grp / groups0);
         const int gid0 = grp0 * L.l0 + tid % L.l0;
@@ -453,10 +461,11 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
             body(&gs, &outv - out_index);
             /* ONE vote: no lane saw anything the uniform recorder cannot take, and all lanes seed the same id */
             int same = 0;
-            __match_all_sync(0xffffffffu, tape.bad ? 0xffffffff00000000ull + (unsigned) lane : tape_uniform_key(tape, outv.id), &same);
+            __match_all_sync(0xffffffffu, (tape.bad || tape_overflowed(tape)) ? 0xffffffff00000000ull + (unsigned) lane
+                                                                              : tape_uniform_key(tape, outv.id), &same);
             /* classify the rows (once per row for the whole warp); a far operand without a far plane is the
                one thing it can still refuse */
-            if (same && tape_classify_uniform(tape.hdr, tape.far_adj, tape.next_id - tape.first_temp, tape.first_temp, tape.wm1)) same = 0;
+            if (same && tape_classify_uniform(tape_hdr(tape), tape.far_adj, tape.next_id - tape.first_temp, tape.first_temp, tape.wm1)) same = 0;
             if (same) {
                 opt_fails = 0;
                 tape_sweep_uniform<MODE>(tape, outv.id, seed, T, pend);
@@ -473,6 +482,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
             /* ---- second copy: the general recorder (also: objective only, tape export) ---- */
             tape_begin(tape, kRecordGeneral);
             body(&gs, &outv - out_index);
+            if (tape_overflowed(tape)) tape.status |= kErrTapeOverflow;
             if (L.retain_meta != nullptr) { /* tape export: leave the rows in the arena for the host */
                 double* m = L.retain_meta + 3 * item;
                 m[0] = outv.value;
@@ -481,7 +491,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
             } else if (L.recording == 1 && __all_sync(0xffffffffu, tape.status == kOk)) {
                 /* a thread whose tape overflowed skips the sweep (the host reports the error) */
                 if (MODE == kAccWarp) param_flush(T.warp_acc, pend);   /* keep the order of the additions fixed */
-                tape.status |= tape_sweep_general<MODE>(tape.rows, tape.id_off, tape.far_adj,
+                tape.status |= tape_sweep_general<MODE>(tape_rows(tape), tape_id_off(), tape.far_adj,
                         tape.next_id - tape.first_temp, tape.first_temp, tape.wm1, outv.id, seed, T,
                         (int) L.cap_slots + kGuardRows, L.sweep_prefetch);
             }
@@ -549,7 +559,8 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
  */
 #define AD4CL_UNPAREN(...) __VA_ARGS__
 #ifndef AD4CL_MIN_BLOCKS
-#define AD4CL_MIN_BLOCKS 3 /* 3 x 256 threads per SM = 80 registers: measured faster than 4 (64 registers spill and rematerialise) */
+#define AD4CL_MIN_BLOCKS 1 /* x AD4CL_MAX_BLOCK = 768 threads per SM = 80 registers, whether launched as 3 x 256 or 1 x 768:
+                              measured faster than 1024 threads (64 registers spill and rematerialise) */
 #endif
 #ifndef AD4CL_ENTRY_SUFFIX
 #define AD4CL_ENTRY_SUFFIX /* the two ahead-of-time builds of one kernel need distinct symbols */
@@ -569,7 +580,7 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
 #if AD4CL_TAPE_STATIC
 #define AD4CL_STATIC_ENTRY_NAME(NAME) AD4CL_CAT4(NAME, __entry, AD4CL_ENTRY_SUFFIX, _s)
 #define AD4CL_STATIC_ENTRY(NAME, PARAMS, ARGS)                                             \
-    extern "C" __global__ void __launch_bounds__(AD4CL_MAX_BLOCK)                           \
+    extern "C" __global__ void __launch_bounds__(AD4CL_STATIC_MAX_BLOCK)                    \
     AD4CL_STATIC_ENTRY_NAME(NAME)(const ad4cl::LaunchInfo L, AD4CL_UNPAREN PARAMS) {        \
         auto body = [&](struct ad_gradient_structure* gs, struct ad_variable* out,         \
                 struct ad_variable* th) __attribute__((always_inline)) {                   \

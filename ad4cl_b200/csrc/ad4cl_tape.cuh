@@ -99,7 +99,7 @@ enum Status : int {
 /* A/B switch for the general sweep: 0 removes the per-batch vote and the warp-uniform batch body (every
    lane always classifies its own id word, as in round 1) */
 #ifndef AD4CL_LANE_UNIFORM_BATCHES
-#define AD4CL_LANE_UNIFORM_BATCHES 1
+#define AD4CL_LANE_UNIFORM_BATCHES 0
 #endif
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -162,8 +162,11 @@ __host__ __device__ inline size_t warp_region_bytes(unsigned cap_slots, bool far
 #endif
 /* 1: the uniform recorder checks warp-uniformity with per-lane hashes compared once per work-item instead
    of a MATCH.ALL vote per push (exact vs 2^-64; measured variant, see profiles/README.md).  Default 0. */
+#ifndef AD4CL_PIN_TAPE
+#define AD4CL_PIN_TAPE 1
+#endif
 #ifndef AD4CL_UNIFORM_HASH
-#define AD4CL_UNIFORM_HASH 0
+#define AD4CL_UNIFORM_HASH 1
 #endif
 
 
@@ -334,16 +337,19 @@ constexpr int kRecordGeneral = 1;
 
 struct ThreadTape {
     int mode;             /* kRecordUniform / kRecordGeneral */
-    char* hdr;            /* header plane of this warp, row 0 (the same address in all lanes) */
-    char* hdr_cur;        /* uniform recorder: header of the next free row */
-    char* cells;          /* this lane's cell column: cell k at cells + 256 k */
-    char* rows;           /* general recorder: this lane's partial in row 0 (row stride kRowBytes) */
-    char* cur;            /* general recorder: this lane's partial in the next free row */
-    int id_off;           /* general recorder: byte offset from a row's partial to its id word, this lane */
+    /* ONE cursor, next_id, addresses every plane: row r = next_id - first_temp has its header at
+       hdr + 8 r, its cell at cells + 256 (2 + r) and its general-recorder row at rows + 384 r.  The bases
+       kept here are biased by -first_temp rows, so an address is one IMAD.WIDE of next_id (and an
+       immediate offset for the later pushes of the same basic block). */
+    char* hdr_b;          /* uniform recorder: header plane of this warp (the same address in all lanes), biased */
+    char* cells_b;        /* uniform recorder: this lane's cell column, biased (row r's cell, not cell 0) */
+    char* rows_b;         /* general recorder: this lane's partials (row stride kRowBytes), biased */
+    char* ids_b;          /* general recorder: this lane's id words (row stride kRowBytes), biased */
     char* far_adj;        /* this lane's far-adjoint column (row stride kFarRowBytes), or null */
-    unsigned cell_off;    /* uniform recorder: byte offset of this lane's next free cell */
     int next_id;          /* first_temp + index of the next free row */
-    int cap_id;           /* first_temp + capacity in slots; kGuardRows guard rows follow */
+    int cap_id;           /* first_temp + capacity in slots + 1: where next_id is clamped (tape_close_op); a
+                             work-item that ends with next_id == cap_id overflowed.  kGuardRows rows follow
+                             the capacity, so the operator that hits the clamp still writes inside the column */
     int first_temp;       /* number of independents: ids >= first_temp are tape positions */
     int wm1;              /* W - 1, W a power of two >= 4 */
     int nops;             /* operators recorded by the current work-item (statistics) */
@@ -354,23 +360,30 @@ struct ThreadTape {
     long long total_slots;
 };
 
+/* the unbiased bases (sweeps, classification, export: once per work-item, not per push) */
+__device__ __forceinline__ char* tape_hdr(const ThreadTape& t) { return t.hdr_b + (long long) t.first_temp * kHdrBytes; }
+__device__ __forceinline__ char* tape_cells(const ThreadTape& t) {
+    return t.cells_b + ((long long) t.first_temp - kUnitCells) * kCellRowBytes;
+}
+__device__ __forceinline__ char* tape_rows(const ThreadTape& t) { return t.rows_b + (long long) t.first_temp * kRowBytes; }
+__device__ __forceinline__ int tape_id_off() { return kRowIdOffset - (int) (threadIdx.x & 31) * 4; }
+
 __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsigned cap_slots,
         int first_temp, int window, bool far) {
     const int lane = threadIdx.x & 31;
     const RegionLayout lay = region_layout(cap_slots, far);
     t.mode = kRecordGeneral;
-    t.hdr = warp_region;
-    t.hdr_cur = warp_region;
-    t.cells = warp_region + lay.off_cells + lane * 8;
+    char* cells = warp_region + lay.off_cells + lane * 8;
     /* the general recorder's rows share the space of the cell plane and the (former) lane-word plane:
        (rows + 2) * 256 + rows * 128 = 512 + rows * 384 bytes */
-    t.rows = t.cells + kUnitCells * kCellRowBytes;
-    t.cur = t.rows;
-    t.id_off = kRowIdOffset - lane * 4;
+    char* rows = cells + kUnitCells * kCellRowBytes;
+    t.hdr_b = warp_region - (long long) first_temp * kHdrBytes;
+    t.cells_b = cells + ((long long) kUnitCells - first_temp) * kCellRowBytes;
+    t.rows_b = rows - (long long) first_temp * kRowBytes;
+    t.ids_b = t.rows_b + (kRowIdOffset - lane * 4);
     t.far_adj = far ? warp_region + lay.off_far + lane * 8 : nullptr;
-    t.cell_off = kUnitCells * kCellRowBytes;
     t.next_id = first_temp;
-    t.cap_id = first_temp + (int) cap_slots;
+    t.cap_id = first_temp + (int) cap_slots + 1;
     t.first_temp = first_temp;
     t.wm1 = window - 1;
     t.nops = 0;
@@ -380,21 +393,28 @@ __device__ __forceinline__ void tape_bind(ThreadTape& t, char* warp_region, unsi
     t.total_ops = 0;
     t.total_slots = 0;
     /* the two constant cells every unit slot of the uniform recorder points at */
-    *reinterpret_cast<double*> (t.cells) = 1.0;
-    *reinterpret_cast<double*> (t.cells + kCellRowBytes) = -1.0;
+    *reinterpret_cast<double*> (cells) = 1.0;
+    *reinterpret_cast<double*> (cells + kCellRowBytes) = -1.0;
+#if AD4CL_PIN_TAPE
+    /* Everything above derives from kernel parameters, and under register pressure the compiler prefers to
+       re-derive it from the constant bank at every push (2-4 extra instructions per push, measured).  Opaque
+       to the optimiser from here on: these stay in registers. */
+    asm volatile("" : "+l"(t.hdr_b), "+l"(t.cells_b), "+l"(t.rows_b), "+l"(t.ids_b));
+    asm volatile("" : "+r"(t.cap_id), "+r"(t.first_temp), "+r"(t.wm1));
+#endif
 }
 
 /* Start recording a work-item (or start over, after a failed optimistic attempt). */
 __device__ __forceinline__ void tape_begin(ThreadTape& t, int mode) {
     t.mode = mode;
-    t.hdr_cur = t.hdr;
-    t.cur = t.rows;
-    t.cell_off = kUnitCells * kCellRowBytes;
     t.next_id = t.first_temp;
     t.nops = 0;
     t.bad = 0;
     t.h1 = t.h2 = 0u;
 }
+
+/* Did the work-item just recorded run out of capacity?  (next_id stopped at the clamp) */
+__device__ __forceinline__ bool tape_overflowed(const ThreadTape& t) { return t.next_id >= t.cap_id; }
 
 /* What the warp votes on after a work-item recorded by the uniform recorder: equal in all 32 lanes (and
    no lane `bad`) <=> the work-item is warp-uniform.  With per-push votes (default) only the seed id is left
@@ -417,12 +437,12 @@ __device__ __forceinline__ unsigned long long tape_uniform_key(const ThreadTape&
  *     constant operand instead of an id the sweep would follow out of the arena.
  * Returns the id word in the low half and Status bits in the high half.
  */
-static __device__ __noinline__ unsigned long long tape_classify_rare(char* rows, int id_off, const char* far_adj,
+static __device__ __noinline__ unsigned long long tape_classify_rare(char* ids, const char* far_adj,
         int id, int first_temp, int row, int flags) {
     const int pos = id - first_temp;
     if (pos < 0 || pos >= row) return (unsigned) (flags | kNopFlag);
     if (far_adj == nullptr) return ((unsigned long long) kErrWindow << 32) | (unsigned) (flags | kNopFlag);
-    atomicOr(reinterpret_cast<int*> (rows + (size_t) pos * kRowBytes + id_off), kHasFarFlag);
+    atomicOr(reinterpret_cast<int*> (ids + (size_t) pos * kRowBytes), kHasFarFlag);
     return (unsigned) (pos | flags | kFarFlag);
 }
 
@@ -459,13 +479,10 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
         __match_all_sync(mask, word, &same);
         t->bad |= (!valid || !same || mask != 0xffffffffu) ? 1 : 0;
 #endif
-        const unsigned aux = UNIT == 0 ? t->cell_off : (UNIT > 0 ? 0u : (unsigned) kCellRowBytes);
-        *reinterpret_cast<int2*> (t->hdr_cur) = make_int2(word, (int) aux);
-        t->hdr_cur += kHdrBytes;
-        if (UNIT == 0) {
-            *reinterpret_cast<double*> (t->cells + t->cell_off) = dx;
-            t->cell_off += kCellRowBytes;
-        }
+        const int aux = UNIT == 0 ? (t->next_id - t->first_temp + kUnitCells) * kCellRowBytes
+                                  : (UNIT > 0 ? 0 : kCellRowBytes);
+        *reinterpret_cast<int2*> (t->hdr_b + (long long) t->next_id * kHdrBytes) = make_int2(word, aux);
+        if (UNIT == 0) *reinterpret_cast<double*> (t->cells_b + (long long) t->next_id * kCellRowBytes) = dx;
         t->next_id++;
     } else {
         const bool is_param = (unsigned) id < (unsigned) t->first_temp;
@@ -475,14 +492,13 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
         const bool reach = (unsigned) (t->next_id - 1 - id) < (unsigned) (t->wm1 - 1);
         int word = (flags & kNopFlag) ? flags : (is_param ? (id | kParamFlag) : (id - t->first_temp)) | flags;
         if (!(flags & kNopFlag) && !is_param && !reach) {
-            const unsigned long long r = tape_classify_rare(t->rows, t->id_off, t->far_adj, id, t->first_temp,
-                    t->next_id - t->first_temp, flags);
+            const unsigned long long r = tape_classify_rare(t->ids_b + (long long) t->first_temp * kRowBytes, t->far_adj,
+                    id, t->first_temp, t->next_id - t->first_temp, flags);
             word = (int) (unsigned) r;
             t->status |= (int) (r >> 32);
         }
-        *reinterpret_cast<double*> (t->cur) = UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0);
-        *reinterpret_cast<int*> (t->cur + t->id_off) = word;
-        t->cur += kRowBytes;
+        *reinterpret_cast<double*> (t->rows_b + (long long) t->next_id * kRowBytes) = UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0);
+        *reinterpret_cast<int*> (t->ids_b + (long long) t->next_id * kRowBytes) = word;
         t->next_id++;
     }
 }
@@ -536,21 +552,13 @@ __device__ __forceinline__ void tape_push2(ThreadTape* t, double dx0, int id0, d
 }
 
 /* Close the operator whose slots were just pushed; returns its result id (the position of its END slot).
-   An operator that does not fit restarts the column at row 0 -- every later access stays inside this
-   thread's own column -- and says so: the uniform recorder hands the work-item to the general one, the
-   general one sets the sticky overflow bit (the sweep is skipped, the host reports the error). */
+   Capacity costs ONE instruction per operator: next_id is clamped at cap_id, so a tape that does not fit
+   keeps overwriting the guard rows behind its column -- every access stays inside this thread's own
+   column -- and the work-item ends with next_id == cap_id (tape_overflowed): the uniform recorder then
+   hands the work-item to the general one, the general one sets the sticky overflow bit (the sweep is
+   skipped, the host reports the error). */
 __device__ __forceinline__ int tape_close_op(ThreadTape* t) {
-    if (t->next_id > t->cap_id) {
-        if (t->mode == kRecordUniform) {
-            t->bad = 1;
-            t->hdr_cur = t->hdr;
-            t->cell_off = kUnitCells * kCellRowBytes;
-        } else {
-            t->status |= kErrTapeOverflow;
-            t->cur = t->rows;
-        }
-        t->next_id = t->first_temp;
-    }
+    t->next_id = min(t->next_id, t->cap_id);
     t->nops++;
     return t->next_id - 1;
 }
@@ -566,12 +574,12 @@ __device__ __forceinline__ void tape_rewind(ThreadTape& t) {
 /* Debug / export accessor: id word and partial of row `row` of this lane's tape. */
 __device__ __forceinline__ void tape_read_row(const ThreadTape* t, int row, double* dx, int* word) {
     if (t->mode == kRecordUniform) {
-        const int2 h = *reinterpret_cast<const int2*> (t->hdr + (size_t) row * kHdrBytes);
+        const int2 h = *reinterpret_cast<const int2*> (tape_hdr(*t) + (size_t) row * kHdrBytes);
         *word = h.x;
-        *dx = *reinterpret_cast<const double*> (t->cells + (unsigned) h.y);
+        *dx = *reinterpret_cast<const double*> (tape_cells(*t) + (unsigned) h.y);
     } else {
-        *word = *reinterpret_cast<const int*> (t->rows + (size_t) row * kRowBytes + t->id_off);
-        *dx = *reinterpret_cast<const double*> (t->rows + (size_t) row * kRowBytes);
+        *word = *reinterpret_cast<const int*> (tape_rows(*t) + (size_t) row * kRowBytes + tape_id_off());
+        *dx = *reinterpret_cast<const double*> (tape_rows(*t) + (size_t) row * kRowBytes);
     }
 }
 
@@ -748,13 +756,14 @@ struct UniformSweep {
             sts_f64(pop_addr, 0.0);
         }
         if (FAR && (word & (kFarFlag | kHasFarFlag))) w = sweep_far_row(far_adj, word, me, w, dx);
-        /* explicit rounding: the product is never contracted into one of the additions below, so the uniform
-           and the general sweep (and every build) perform the same roundings per lane */
-        const double c = __dmul_rn(w, dx);
+        /* explicit rounding, the same in every sweep (and every build): a temporary's adjoint takes ONE fused
+           multiply-add per slot, an independent's contribution is the rounded product (it is reduced over
+           the warp before it is added) */
         if ((word & (kNopFlag | kParamFlag | kFarFlag)) == 0) { /* a recent temporary: its ring entry */
             const unsigned a = T.ring + (((unsigned) word << 3) & wmask8);
-            sts_f64(a, __dadd_rn(lds_f64(a), c));
+            sts_f64(a, __fma_rn(w, dx, lds_f64(a)));
         }
+        const double c = __dmul_rn(w, dx);
         if (word & kParamFlag) {
             const int id = word & kIdMask;
             if (MODE == kAccThread) {
@@ -787,15 +796,15 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, do
     const int nb = (rows + 3) >> 2;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        if (rows + j < 4 * nb) *reinterpret_cast<int2*> (t.hdr + (size_t) (rows + j) * kHdrBytes) = make_int2(kNopFlag, 0);
+        if (rows + j < 4 * nb) *reinterpret_cast<int2*> (tape_hdr(t) + (size_t) (rows + j) * kHdrBytes) = make_int2(kNopFlag, 0);
     }
     /* (W - 1) << 3, pinned in a register (the compiler otherwise re-derives it from the launch
        parameters in the constant bank at every use) */
     unsigned wmask8 = (unsigned) t.wm1 << 3;
     asm volatile("" : "+r"(wmask8));
     /* likewise the two plane pointers (otherwise re-derived from the launch parameters every batch) */
-    const char* hdr = t.hdr;
-    const char* cells = t.cells;
+    const char* hdr = tape_hdr(t);
+    const char* cells = tape_cells(t);
     asm volatile("" : "+l"(hdr), "+l"(cells));
     UniformSweep<MODE> S{hdr, cells, t.far_adj, T, wmask8, 0.0, pend};
 
@@ -949,11 +958,11 @@ static __device__ __noinline__ int tape_sweep_general(const char* rows_base, int
                     sts_f64(r, 0.0);
                 }
                 if (idw & (kFarFlag | kHasFarFlag)) w = sweep_far_lane(far_adj, idw, me, w, dx_now[j]);
-                const double c = __dmul_rn(w, dx_now[j]);
                 if ((idw & (kNopFlag | kParamFlag | kFarFlag)) == 0) {
                     const unsigned a = T.ring + ((unsigned) (idw & wmask) << 3);
-                    sts_f64(a, __dadd_rn(lds_f64(a), c));
+                    sts_f64(a, __fma_rn(w, dx_now[j], lds_f64(a)));
                 }
+                const double c = __dmul_rn(w, dx_now[j]);
                 if ((idw & (kNopFlag | kParamFlag)) == kParamFlag) {
                     const int id = idw & kIdMask;
                     if (MODE == kAccThread) {
@@ -988,7 +997,8 @@ static __device__ __noinline__ int tape_sweep_general(const char* rows_base, int
                        other class adds to the pad entry of this thread's ring (index W), which nothing reads. */
                     unsigned a = T.ring + (cls == 0 ? ((unsigned) (payload & wmask) << 3) : pad_off);
                     if (MODE == kAccThread) a = cls == kParamFlag ? T.thread_acc + (unsigned) payload * T.stride : a;
-                    sts_f64(a, __dadd_rn(lds_f64(a), c));
+                    sts_f64(a, (MODE == kAccThread && cls == kParamFlag) ? __dadd_rn(lds_f64(a), c)
+                                                                          : __fma_rn(w, dx_now[j], lds_f64(a)));
                 }
                 if (MODE != kAccThread) sweep_param<MODE>(T, cls == kParamFlag, payload, c);
             }

@@ -193,6 +193,18 @@ struct ad4cl_kernel {
     int nparams = -1;
     int block = 0, grid = 0;
     size_t smem = 0, arena_bytes = 0;
+    /* Launch shapes the tuner may choose between: [0] the configured (or default 256-thread) work-group,
+       [1] one 768-thread work-group per SM, offered when the caller left the work-group size to the
+       library (OpenCL's local_work_size == NULL).  Same number of resident warps, same arena. */
+    struct Shape { int block = 0, grid = 0, l0 = 0; size_t smem = 0; long long g0 = 0, n_items = 0; };
+    Shape shapes[2];
+    int nshapes = 1, shape = 0;
+    void use_shape(int i) {
+        shape = i;
+        block = shapes[i].block; grid = shapes[i].grid; smem = shapes[i].smem;
+        L.l0 = shapes[i].l0; L.g0 = (int) shapes[i].g0; L.n_items = shapes[i].n_items;
+        stats.grid = grid; stats.block = block; stats.smem_bytes = smem;
+    }
     int launches_per_eval = 1;
     const double* seeds_dev = nullptr;   /* set around one enqueue by ad4cl_cuda_eval_general */
     double* out_values_dev = nullptr;
@@ -275,12 +287,12 @@ ad4cl_kernel* new_kernel(ad4cl_context* ctx, const char* name, const char* sig) 
 int occupancy(ad4cl_kernel* k, int block, size_t smem, int* blocks) {
     /* the entry's static shared memory (~3 KB) counts against the 48 KB default as well: opt in early */
     if (!k->module) {
-        if (smem > 40 * 1024)
+        if (smem > 36 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(k->entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k->entry, block, smem));
     } else {
         DriverApi& d = driver();
-        if (smem > 40 * 1024) {
+        if (smem > 36 * 1024) {
             CUresult r = d.cuFuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) smem);
             if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed: %d", smem, (int) r);
         }
@@ -340,6 +352,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
             if (r->nparams != nparams) continue;
             bool ok = (unsigned) r->slots <= cap_slots;   /* a deliberately short tape keeps its overflow report */
             if (g1 != 1) ok = false;                      /* the instances are 1-D kernels */
+            if (block > AD4CL_STATIC_MAX_BLOCK) ok = false; /* ... built for work-groups of at most 256 */
             /* AUTO leaves explicit choices of the arena machinery alone */
             if (tier == AD4CL_TAPE_AUTO && (c.window != 0 || c.far_plane == 0
                     || (c.acc_mode != AD4CL_ACC_AUTO && c.acc_mode != AD4CL_ACC_THREAD))) ok = false;
@@ -403,14 +416,54 @@ int prepare(ad4cl_kernel* k, int nparams) {
     const long long ngroups = (g0 / l0) * (g1 / l1);
     int grid = (int) std::min<long long>((long long) k->ctx->prop.multiProcessorCount * per_sm, ngroups);
     grid = std::max(grid, 1);
+    k->shapes[0] = {block, grid, l0, smem, g0, g0 * g1};
+    k->nshapes = 1;
+
+    /* The alternative shape: ONE work-group of AD4CL_MAX_BLOCK threads per SM.  With the work-groups in
+       lock step (LaunchInfo::lockstep) all resident warps then walk the same stretch of a long objective
+       together, which is what a body larger than the instruction caches wants (profiles/README.md).
+       Only when the caller left the work-group size open, for 1-D arena kernels. */
+    if (!srow && tier == AD4CL_TAPE_HBM && c.local_size[0] <= 0 && g1 == 1 && c.blocks_per_sm <= 0
+            && AD4CL_MAX_BLOCK > block && c.global_size[0] >= (long long) AD4CL_MAX_BLOCK * k->ctx->prop.multiProcessorCount) {
+        const int b2 = AD4CL_MAX_BLOCK;
+        const size_t smem2 = ad4cl::entry_smem_bytes(b2, nparams, window, acc, false, cap_slots, far);
+        if (smem2 <= k->ctx->prop.sharedMemPerBlockOptin) {
+            int ps = 0, ps2 = 0;
+            rc = occupancy(k, b2, smem2, &ps);
+            if (rc != AD4CL_OK) return rc;
+            const int other = 1 - k->recorder;
+            if (k->module ? k->functions[other][acc] != nullptr : k->entries[other][acc] != nullptr) {
+                const void* e0 = k->entry;
+                CUfunction f0 = k->function;
+                if (k->module) k->function = k->functions[other][acc];
+                else k->entry = k->entries[other][acc];
+                rc = occupancy(k, b2, smem2, &ps2);
+                k->entry = e0;
+                k->function = f0;
+                if (rc != AD4CL_OK) return rc;
+                ps = std::min(ps, ps2);
+            }
+            const long long g0b = (c.global_size[0] + b2 - 1) / b2 * b2;
+            if (ps >= 1 && g0b < (1LL << 31) && ps * b2 >= per_sm * block) { /* never fewer resident warps */
+                const int grid2 = (int) std::min<long long>((long long) k->ctx->prop.multiProcessorCount * ps, g0b / b2);
+                k->shapes[1] = {b2, grid2, b2, smem2, g0b, g0b};
+                k->nshapes = 2;
+            }
+        }
+    }
+    int max_grid = grid, max_warps = grid * (block / 32);
+    if (k->nshapes > 1) {
+        max_grid = std::max(max_grid, k->shapes[1].grid);
+        max_warps = std::max(max_warps, k->shapes[1].grid * (k->shapes[1].block / 32));
+    }
 
     const size_t region = ad4cl::warp_region_bytes(cap_slots, far);
-    const size_t arena_bytes = tier != AD4CL_TAPE_HBM ? 0 : (size_t) grid * (block / 32) * region;
+    const size_t arena_bytes = tier != AD4CL_TAPE_HBM ? 0 : (size_t) max_warps * region;
     const int ncols = nparams + 3;
     const int pcols = (acc == AD4CL_ACC_GLOBAL ? 0 : nparams) + 3; /* columns of the per-block partials */
 
     CUDA_TRY(cudaMalloc(&k->params_dev, sizeof (struct ad_variable) * (size_t) std::max(nparams, 1)));
-    CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) grid * pcols));
+    CUDA_TRY(cudaMalloc(&k->partials, sizeof (double) * (size_t) max_grid * pcols));
     CUDA_TRY(cudaMalloc(&k->result_dev, sizeof (double) * (size_t) (ncols + 1)));
     CUDA_TRY(cudaMalloc(&k->status_dev, sizeof (int)));
     CUDA_TRY(cudaMemset(k->status_dev, 0, sizeof (int)));
@@ -420,7 +473,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
         if (e != cudaSuccess) {
             cudaGetLastError();
             return fail(AD4CL_ERR_NOMEM, "tape arena of %zu bytes (%d warps x %zu) does not fit: lower blocks_per_sm or max_ops",
-                    arena_bytes, grid * (block / 32), region);
+                    arena_bytes, max_warps, region);
         }
         CUDA_TRY(cudaMemset(k->arena, 0, arena_bytes)); /* far bitmaps must start clear */
     }
@@ -434,12 +487,10 @@ int prepare(ad4cl_kernel* k, int nparams) {
     if (!k->ev1) CUDA_TRY(cudaEventCreate(&k->ev1));
 
     ad4cl::LaunchInfo& L = k->L;
-    L.n_items = g0 * g1;
-    L.g0 = (int) g0;
     L.g0_user = (int) c.global_size[0];
     L.n_user = c.global_size[0] * (c.global_size[1] > 0 ? c.global_size[1] : 1);
-    L.l0 = l0;
     L.nparams = nparams;
+    L.lockstep = c.lockstep == AD4CL_LOCKSTEP_OFF ? 0 : 1;
     L.recording = 1;
     L.acc_mode = acc;
     L.window = window;
@@ -447,7 +498,8 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
     L.sweep_prefetch = c.sweep_prefetch == AD4CL_PREFETCH_ON ? 1 : 0;
     /* AUTO: decided by autotune_recorder on the first gradient evaluation (the register tier has no choice to make) */
-    k->tune_pending = !srow && (c.recorder == AD4CL_RECORDER_AUTO || c.sweep_prefetch == AD4CL_PREFETCH_AUTO);
+    k->tune_pending = !srow && (c.recorder == AD4CL_RECORDER_AUTO || c.sweep_prefetch == AD4CL_PREFETCH_AUTO
+                                || c.lockstep == AD4CL_LOCKSTEP_AUTO || k->nshapes > 1);
     k->stats.recorder = k->tune_pending && c.recorder == AD4CL_RECORDER_AUTO ? -1 : (srow ? -1 : k->recorder);
     k->stats.sweep_prefetch = k->tune_pending && c.sweep_prefetch == AD4CL_PREFETCH_AUTO ? -1 : L.sweep_prefetch;
     L.cap_slots = cap_slots;
@@ -460,14 +512,10 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.comm.world = 1;
     k->fused = fused;
 
-    k->block = block;
-    k->grid = grid;
-    k->smem = smem;
     k->arena_bytes = arena_bytes;
     k->nparams = nparams;
-    k->stats.grid = grid;
-    k->stats.block = block;
-    k->stats.smem_bytes = smem;
+    k->use_shape(0);
+    k->stats.lockstep = L.lockstep;
     k->stats.arena_bytes = arena_bytes;
     k->stats.tape_tier = tier;
     k->ready = true;
@@ -634,9 +682,10 @@ int autotune_recorder(ad4cl_kernel* k, const double* theta_dev) {
         return AD4CL_OK; /* a caller-owned stream under graph capture cannot be timed: decide on a later call */
     }
     k->tune_pending = false;
-    struct Cand { int recorder, prefetch; float ms; };
+    struct Cand { int recorder, prefetch, shape, lockstep; float ms; };
     std::vector<Cand> cands;
     const ad4cl_kernel_config& c = k->cfg;
+    const int ls0 = c.lockstep == AD4CL_LOCKSTEP_OFF ? 0 : 1;
     for (int rec = 0; rec < 2; rec++) {
         if (c.recorder != AD4CL_RECORDER_AUTO && (c.recorder == AD4CL_RECORDER_LANE) != (rec == 1)) continue;
         if (rec == 0 && k->module && k->functions[0][k->acc] == nullptr) continue;
@@ -644,17 +693,26 @@ int autotune_recorder(ad4cl_kernel* k, const double* theta_dev) {
             if (rec == 0 && pf == 1) continue; /* the uniform sweep has no prefetch */
             if (rec == 1 && c.sweep_prefetch != AD4CL_PREFETCH_AUTO && (c.sweep_prefetch == AD4CL_PREFETCH_ON) != (pf == 1)) continue;
             if (k->L.tape_in_smem && pf == 1) continue;
-            cands.push_back({rec, pf, 1e30f});
+            for (int sh = 0; sh < k->nshapes; sh++) {
+                if (sh == 1 && (rec == 1 || !ls0)) continue; /* the one-group-per-SM shape pays with the uniform recorder in lock step only (measured) */
+                cands.push_back({rec, pf, sh, ls0, 1e30f});
+            }
         }
     }
-    if (cands.size() > 1) {
+    auto apply = [&](const Cand& cd) {
+        k->recorder = cd.recorder;
+        if (k->module) k->function = k->functions[k->recorder][k->acc];
+        else k->entry = k->entries[k->recorder][k->acc];
+        k->L.sweep_prefetch = cd.prefetch;
+        k->L.lockstep = cd.lockstep;
+        k->use_shape(cd.shape);
+    };
+    auto time_all = [&](std::vector<Cand>& cs, size_t from) -> int {
         for (int round = 0; round < 2; round++) {
-            for (Cand& cd : cands) {
+            for (size_t i = from; i < cs.size(); i++) {
+                Cand& cd = cs[i];
                 if (round == 1 && cd.ms > 200.f && cd.ms < 1e29f) continue;
-                k->recorder = cd.recorder;
-                if (k->module) k->function = k->functions[k->recorder][k->acc];
-                else k->entry = k->entries[k->recorder][k->acc];
-                k->L.sweep_prefetch = cd.prefetch;
+                apply(cd);
                 CUDA_TRY(cudaEventRecord(k->ev0, st));
                 int rc = enqueue(k, theta_dev, k->result_dev, 1, 0);
                 if (rc != AD4CL_OK) return rc;
@@ -665,16 +723,33 @@ int autotune_recorder(ad4cl_kernel* k, const double* theta_dev) {
                 if (round == 1 || ms > 200.f) cd.ms = std::min(cd.ms, ms);
             }
         }
+        return AD4CL_OK;
+    };
+    auto best_of = [&]() {
+        size_t b = 0;
+        for (size_t i = 1; i < cands.size(); i++)
+            if (cands[i].ms < cands[b].ms) b = i;
+        return b;
+    };
+    if (cands.size() > 1 || c.lockstep == AD4CL_LOCKSTEP_AUTO) {
+        int rc = time_all(cands, 0);
+        if (rc != AD4CL_OK) return rc;
+        if (c.lockstep == AD4CL_LOCKSTEP_AUTO && cands[best_of()].shape == 0) {
+            /* second stage: the winner without the per-work-group barrier (work-items of very different
+               lengths in one work-group, or a body that fits the instruction cache anyway) */
+            Cand free_running = cands[best_of()];
+            free_running.lockstep = 0;
+            free_running.ms = 1e30f;
+            cands.push_back(free_running);
+            rc = time_all(cands, cands.size() - 1);
+            if (rc != AD4CL_OK) return rc;
+        }
     }
-    const Cand* best = &cands[0];
-    for (const Cand& cd : cands)
-        if (cd.ms < best->ms) best = &cd;
-    k->recorder = best->recorder;
-    if (k->module) k->function = k->functions[k->recorder][k->acc];
-    else k->entry = k->entries[k->recorder][k->acc];
-    k->L.sweep_prefetch = best->prefetch;
+    const Cand best = cands[best_of()];
+    apply(best);
     k->stats.recorder = k->recorder;
     k->stats.sweep_prefetch = k->L.sweep_prefetch;
+    k->stats.lockstep = k->L.lockstep;
     CUDA_TRY(cudaMemsetAsync(k->status_dev, 0, sizeof (int), st)); /* an error shows up again in the evaluation proper */
     return AD4CL_OK;
 }
@@ -1062,6 +1137,7 @@ int ad4cl_cuda_kernel_config_default(ad4cl_kernel_config* cfg) {
     cfg->epilogue = AD4CL_EPILOGUE_SUM;
     cfg->sweep_prefetch = AD4CL_PREFETCH_AUTO;
     cfg->recorder = AD4CL_RECORDER_AUTO;
+    cfg->lockstep = AD4CL_LOCKSTEP_AUTO;
     return AD4CL_OK;
 }
 

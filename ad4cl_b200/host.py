@@ -28,6 +28,7 @@ ACC = {"auto": -1, "thread": 0, "warp": 1, "global": 2}
 TAPE = {"auto": -1, "hbm": 0, "shared": 1, "register": 2}
 PREFETCH = {"auto": -1, "off": 0, "on": 1}
 RECORDER = {"auto": -1, "uniform": 0, "lane": 1}
+LOCKSTEP = {"auto": -1, "off": 0, "on": 1}
 EPILOGUE = {"sum": 0, "half_n_log": 1}
 
 
@@ -41,7 +42,8 @@ class KernelConfig(ctypes.Structure):
     _fields_ = [("global_size", c_longlong * 2), ("local_size", c_int * 2), ("max_ops", c_int),
                 ("max_slots", c_int), ("window", c_int), ("far_plane", c_int), ("acc_mode", c_int),
                 ("tape_tier", c_int), ("epilogue", c_int), ("epilogue_n", c_double),
-                ("blocks_per_sm", c_int), ("reference_quirks", c_int), ("sweep_prefetch", c_int), ("recorder", c_int)]
+                ("blocks_per_sm", c_int), ("reference_quirks", c_int), ("sweep_prefetch", c_int), ("recorder", c_int),
+                ("lockstep", c_int)]
 
 
 class LbfgsOptions(ctypes.Structure):
@@ -57,7 +59,8 @@ class LbfgsResult(ctypes.Structure):
 class EvalStats(ctypes.Structure):
     _fields_ = [("ops", c_double), ("slots", c_double), ("grid", c_int), ("block", c_int),
                 ("smem_bytes", c_size_t), ("arena_bytes", c_size_t), ("kernel_ms", c_float),
-                ("sweep_prefetch", c_int), ("tape_tier", c_int), ("recorder", c_int)]
+                ("sweep_prefetch", c_int), ("tape_tier", c_int), ("recorder", c_int),
+                ("lockstep", c_int)]
 
 
 def _load() -> ctypes.CDLL:
@@ -230,7 +233,7 @@ class Kernel:
     def configure(self, global_size, max_ops: int, *, local_size=None, max_slots: int = 0, window: int = 0,
                   far_plane: bool = True, acc: str = "auto", tape: str = "auto", epilogue: str = "sum",
                   epilogue_n: float = 0.0, blocks_per_sm: int = 0, prefetch: str = "auto",
-                  recorder: str = "auto") -> "Kernel":
+                  recorder: str = "auto", lockstep: str = "auto") -> "Kernel":
         cfg = KernelConfig()
         _check(lib.ad4cl_cuda_kernel_config_default(byref(cfg)))
         gs = (global_size, 1) if np.isscalar(global_size) else tuple(global_size)
@@ -245,6 +248,7 @@ class Kernel:
         cfg.blocks_per_sm = int(blocks_per_sm)
         cfg.sweep_prefetch = PREFETCH[prefetch]
         cfg.recorder = RECORDER[recorder]
+        cfg.lockstep = LOCKSTEP[lockstep]
         _check(lib.ad4cl_cuda_kernel_configure(self._h, byref(cfg)))
         return self
 
@@ -337,7 +341,8 @@ class Kernel:
         return {"ops": s.ops, "slots": s.slots, "grid": s.grid, "block": s.block, "smem_bytes": s.smem_bytes,
                 "arena_bytes": s.arena_bytes, "kernel_ms": s.kernel_ms, "sweep_prefetch": s.sweep_prefetch,
                 "tape_tier": {v: k for k, v in TAPE.items()}.get(s.tape_tier, str(s.tape_tier)),
-                "recorder": {v: k for k, v in RECORDER.items()}.get(s.recorder, str(s.recorder)) if s.recorder >= 0 else "n/a"}
+                "recorder": {v: k for k, v in RECORDER.items()}.get(s.recorder, str(s.recorder)) if s.recorder >= 0 else "n/a",
+                "lockstep": int(s.lockstep)}
 
     def profile(self, enable: bool = True) -> None:
         """CUDA-event timing of the fused kernel alone (CL_PROFILING analogue)."""

@@ -435,6 +435,8 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--prefetch", default="auto", choices=["auto", "off", "on"],
                     help="sweep L2 prefetch (auto: the library times both on the first evaluation)")
+    ap.add_argument("--lockstep", default="auto", choices=["auto", "on", "off"],
+                    help="work-groups in lock step (one barrier per work-item): keeps the warps' instruction fetches together")
     ap.add_argument("--recorder", default="auto", choices=["auto", "uniform", "lane"],
                     help="tape recorder (auto: the library times uniform / lane / lane + prefetch on the first evaluation)")
     ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
@@ -505,6 +507,8 @@ def main():
         cfg["prefetch"] = args.prefetch
     if args.recorder != "auto":
         cfg["recorder"] = args.recorder
+    if args.lockstep != "auto":
+        cfg["lockstep"] = args.lockstep
     k = W.bind(ctx, w, **cfg)
 
     theta_host = torch.from_numpy(np.ascontiguousarray(w.theta)).pin_memory()
@@ -672,7 +676,7 @@ def main():
                            l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
                            tape_tier=stats["tape_tier"], acc_mode=args.acc, launches_per_eval=k.launches_per_eval,
-                           recorder=stats["recorder"], sweep_prefetch=stats["sweep_prefetch"],
+                           recorder=stats["recorder"], sweep_prefetch=stats["sweep_prefetch"], lockstep=stats["lockstep"],
                            recorder_choice="auto-tuned on the first evaluation" if args.recorder == "auto" else "forced"),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     # ad4cl_cuda_eval / ad4cl_cuda_eval_sharded: P doubles up, [grad, f, ops, slots, status] down,

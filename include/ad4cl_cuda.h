@@ -89,14 +89,26 @@ enum {
      UNIFORM  optimistic: ONE 8-byte header per warp and slot + an 8-byte cell per lane only for partials that
               are not +1/-1 (a third of the bytes; short tapes never leave L2); a warp whose lanes turn out to
               record different tapes re-records the work-item with the LANE recorder.
-     LANE     the round-1 stream, 12 bytes per lane and slot; its sweep detects warp-uniform batches itself.
-     AUTO     times UNIFORM, LANE and LANE + prefetch on the first gradient evaluation of a configured kernel
-              (six extra evaluations, once) and keeps the fastest.  Never changes a result beyond the order in
-              which an independent's contributions are summed over a warp (bit-identical with <= 16 independents). */
+     LANE     the round-1 stream, 12 bytes per lane and slot: any control flow, any ids.
+     AUTO     the first gradient evaluation of a configured kernel times the candidates -- UNIFORM (in both
+              launch shapes when the work-group size was left open), LANE, LANE + prefetch, then the winner
+              without the lock-step barrier -- twice each, once, and keeps the fastest.  Never changes a
+              result beyond the order in which an independent's contributions are summed over a warp
+              (bit-identical with <= 16 independents). */
 enum {
     AD4CL_RECORDER_AUTO = -1,
     AD4CL_RECORDER_UNIFORM = 0,
     AD4CL_RECORDER_LANE = 1
+};
+
+/* Lock step: the warps of a work-group wait for each other before every work-item.  The objective body of
+   a statistical model is tens of KB of straight-line code, more than the 32 KB L1.5 instruction cache;
+   24 warps at 24 different places in it starve on instruction fetch (ncu: stall_no_instruction), warps
+   that walk it together share their fetches.  Costs a barrier per work-item: AUTO measures it. */
+enum {
+    AD4CL_LOCKSTEP_AUTO = -1,
+    AD4CL_LOCKSTEP_OFF = 0,
+    AD4CL_LOCKSTEP_ON = 1
 };
 
 /* scalar epilogue applied to S = sum_i out_i */
@@ -107,7 +119,8 @@ enum {
 
 typedef struct ad4cl_kernel_config {
     long long global_size[2];  /* NDRange; global_size[1] = 1 for 1-D */
-    int local_size[2];         /* work-group; product <= 256; {0,0} = runtime's choice */
+    int local_size[2];         /* work-group; product <= 768 and a multiple of 32; {0,0} = runtime's choice: 256
+                                  (16 x 16 for 2-D), or one 768-thread group per SM if that measures faster */
     int max_ops;               /* most AD operators one work-item records */
     int max_slots;             /* most operand slots (sum of k) one work-item records; 0 = 2*max_ops */
     int window;                /* adjoint ring entries (power of two); 0 = runtime's choice */
@@ -120,6 +133,7 @@ typedef struct ad4cl_kernel_config {
     int reference_quirks;      /* builtin kernels only: 1 = reference arithmetic as written */
     int sweep_prefetch;        /* AD4CL_PREFETCH_* */
     int recorder;              /* AD4CL_RECORDER_* */
+    int lockstep;              /* AD4CL_LOCKSTEP_* */
 } ad4cl_kernel_config;
 
 typedef struct ad4cl_eval_stats {
@@ -132,6 +146,7 @@ typedef struct ad4cl_eval_stats {
     int sweep_prefetch;     /* the setting in use: 0 off, 1 on, -1 not decided yet (AUTO before the first gradient evaluation) */
     int tape_tier;          /* the AD4CL_TAPE_* tier in use (what AUTO resolved to) */
     int recorder;           /* the AD4CL_RECORDER_* in use, -1 not decided yet */
+    int lockstep;           /* 1: work-groups run in lock step */
 } ad4cl_eval_stats;
 
 int ad4cl_cuda_init(int device, ad4cl_context** ctx);

@@ -1,0 +1,24 @@
+mkdir -p gpurun_out
+run() { # lib, label, bench args...
+  lib=$1; label=$2; shift 2
+  AD4CL_CUDA_LIB=$PWD/$lib timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra "$@" 2>gpurun_out/err.log | python -c "
+import sys, json
+try:
+    d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+    l = d['launch']
+    print('$lib', '$label', 'kernel_ms=%.4f' % d['roofline']['kernel_ms'], 'evals/s=%.2f' % d['value'], 'e2e=%.2f' % d['e2e']['value'], l['grid'], l['block'], l['smem_bytes'], l['recorder'], l['sweep_prefetch'])
+except Exception as e:
+    print('$lib', '$label', 'FAILED', repr(e)); print(open('gpurun_out/err.log').read()[-600:])
+"
+}
+for ls in 768 512 1024; do
+  run variants/big.so caa-uniform-$ls --recorder uniform --local-size $ls --workload catch_at_age --n 10000000
+  run variants/big.so caa-lane-pf1-$ls --recorder lane --prefetch on --local-size $ls --workload catch_at_age --n 10000000
+done 2>&1 | tee gpurun_out/r02k_ab.log
+run variants/big.so ts-uniform-768 --recorder uniform --local-size 768 --workload tape_stress --n 10000000 --tape-steps 333 | tee -a gpurun_out/r02k_ab.log
+M=gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active
+for s in long_scoreboard short_scoreboard wait no_instruction math_pipe_throttle branch_resolving barrier not_selected; do M=$M,smsp__average_warps_issue_stalled_${s}_per_issue_active.ratio; done
+for rec in uniform lane; do
+  AD4CL_CUDA_LIB=$PWD/variants/lockstep.so timeout 300 ncu --metrics $M --clock-control none -k regex:catch_at_age -c 1 --csv --log-file gpurun_out/r02k_ncu_$rec.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra --recorder $rec --prefetch on --workload catch_at_age --n 10000000 > gpurun_out/r02k_ncu.log 2>&1
+  echo == lockstep $rec; grep -v "^==" gpurun_out/r02k_ncu_$rec.csv | awk -F'","' '{print $13, $15}' | grep -v "Metric Name"
+done
