@@ -277,19 +277,16 @@ __device__ __forceinline__ void run_objective_static(const LaunchInfo& L, Body&&
     long long total_ops = 0, total_slots = 0;
     int status = kOk;
     const long long ngroups = (L.n_items + B - 1) / B;
-    const int groups0 = L.g0 / L.l0;
-    const int l1 = B / L.l0;
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         /* a FRESH tape per work-item: nothing loop-carried stands between the stores of the forward
            pass and the loads of the sweep, so the compiler sees the id words as the constants they are */
         ThreadTape tape;
         tape_bind_static(tape);
-        const int grp0 = (int) (grp % groups0), grp1 = (int) (grp / groups0);
-        const int gid0 = grp0 * L.l0 + tid % L.l0;
-        const int gid1 = grp1 * l1 + tid / L.l0;
+        /* the register-tier instances are 1-D kernels (the shim checks): no 64-bit division per work-item,
+           out[get_global_id(0)] */
+        const int gid0 = (int) grp * B + tid;
         ad4cl_item_ids[tid].gid0 = gid0;
-        ad4cl_item_ids[tid].gid1 = gid1;
-        /* the register-tier instances are 1-D kernels (the shim checks): out[get_global_id(0)] */
+        ad4cl_item_ids[tid].gid1 = 0;
         const long long out_index = gid0;
 
         struct ad_gradient_structure gs;
@@ -423,15 +420,22 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
     const long long ngroups = (L.n_items + B - 1) / B;
     const int groups0 = L.g0 / L.l0;           /* work-groups along dimension 0 */
     const int l1 = B / L.l0;
+    const bool one_d = L.l0 == B && (long long) groups0 == ngroups;
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         /* lock step: keep the warps of a CTA inside the same work-item's code -- 3 (or 1) fetch streams
            per SM instead of 24; the hot code of a long objective is larger than the 32 KB L1.5 instruction
            cache and the warps otherwise starve on instruction fetch (profiles/README.md) */
         if (L.lockstep) __syncthreads();
         /* NDRange coordinates of this thread's work-item in work-group `grp` */
-        const int grp0 = (int) (grp % groups0), grp1 = (int) (grp / groups0);
-        const int gid0 = grp0 * L.l0 + tid % L.l0;
-        const int gid1 = grp1 * l1 + tid / L.l0;
+        int gid0, gid1;
+        if (one_d) { /* no 64-bit division per work-item */
+            gid0 = (int) grp * B + tid;
+            gid1 = 0;
+        } else {
+            const int grp0 = (int) (grp % groups0), grp1 = (int) (grp / groups0);
+            gid0 = grp0 * L.l0 + tid % L.l0;
+            gid1 = grp1 * l1 + tid / L.l0;
+        }
         ad4cl_item_ids[tid].gid0 = gid0;
         ad4cl_item_ids[tid].gid1 = gid1;
         const long long item = (long long) gid1 * L.g0 + gid0;
