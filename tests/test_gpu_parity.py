@@ -153,3 +153,42 @@ def test_recorder_and_prefetch_choices_do_not_change_the_result(ctx, name, n, kw
         else:
             assert abs(f - base[0]) <= 1e-13 * abs(base[0])
             assert np.max(np.abs(g - base[1])) <= 1e-13 * np.max(np.abs(base[1]))
+
+
+@pytest.mark.parametrize("name,n,kw", [("catch_at_age", 200400, {}), ("tape_stress", 150001, {"steps": 40})],
+                         ids=["catch_at_age", "tape_stress"])
+def test_launch_shape_and_lock_step_do_not_change_the_result(ctx, oracle_api, name, n, kw):
+    """AD4CL_LOCKSTEP_* and the launch shape (include/ad4cl_cuda.h: the configured work-group, or ONE 768-thread
+    work-group per SM when the size is left to the library) are performance choices as well: on a ragged
+    problem large enough for the 768-thread shape to be offered, every combination of recorder, work-group size
+    and lock step agrees with the reference runtime at 1e-12, the barrier alone never changes a bit, and what AUTO
+    settles on is one of the measured candidates."""
+    w = W.describe(name, n, **kw)
+    ref, _ = oracle_eval(oracle_api, w, False)
+    ref_f, ref_g = ref["f"], np.asarray(ref["grad"])
+    scale = np.max(np.abs(ref_g))
+    out = {}
+    for rec in ("uniform", "lane"):
+        for ls in (256, 768, 96):
+            for step in ("on", "off"):
+                k = W.bind(ctx, w, recorder=rec, prefetch="off", tape="hbm", local_size=ls, lockstep=step)
+                try:
+                    f, g = k.eval(w.theta)
+                    st = k.stats()
+                    assert st["block"] == ls and st["lockstep"] == (1 if step == "on" else 0) and st["recorder"] == rec
+                    assert abs(f - ref_f) <= 1e-12 * abs(ref_f) and np.max(np.abs(g - ref_g)) <= 1e-12 * scale
+                    out[(rec, ls, step)] = (f, g)
+                finally:
+                    k.free()
+            assert out[(rec, ls, "on")][0] == out[(rec, ls, "off")][0]
+            assert np.array_equal(out[(rec, ls, "on")][1], out[(rec, ls, "off")][1])
+    k = W.bind(ctx, w, tape="hbm")                          # everything left to the library
+    try:
+        f, g = k.eval(w.theta)
+        st = k.stats()
+        assert st["block"] in (256, 768) and st["lockstep"] in (0, 1) and st["recorder"] in ("uniform", "lane")
+        assert abs(f - ref_f) <= 1e-12 * abs(ref_f) and np.max(np.abs(g - ref_g)) <= 1e-12 * scale
+        f2, g2 = k.eval(w.theta)
+        assert f == f2 and np.array_equal(g, g2)
+    finally:
+        k.free()
