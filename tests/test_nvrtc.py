@@ -162,3 +162,55 @@ def test_matrix_golden_256(ctx):
     gA = np.repeat(B.reshape(n, n).sum(axis=1)[None, :], n, axis=0).ravel()
     gB = np.repeat(A.reshape(n, n).sum(axis=0)[:, None], n, axis=1).ravel()
     assert rel_err(g, np.concatenate([gA, gB])) <= RTOL
+
+
+PRIVATE_OVERFLOW_SRC = r"""
+__kernel void private_chain(__global struct ad_gradient_structure* gs,
+        __global struct ad_entry* gradient_stack,
+        __constant struct ad_variable* theta,
+        __global double* x,
+        __global struct ad_variable* out, int size, int links) {
+    ad_init(gs, gradient_stack);
+    const int id = get_global_id(0);
+    if (id < size) {
+        struct ad_private_gradient_structure p;
+        ad_init_p(&p);
+        p.current_ad_variable_id = gs->current_ad_variable_id;
+        struct ad_variable v = ad_times_vd_p(&p, theta[0], x[id]);
+        for (int j = 0; j < links; j++) v = ad_plus_p(&p, ad_times_vd_p(&p, v, 0.5), theta[1]);
+        out[id] = ad_commit_p(gs, &p, v);
+    }
+}
+"""
+
+
+@pytest.mark.gpu
+def test_private_stack_overflow_is_reported_not_clipped(ctx):
+    """ad_private_gradient_structure (ad.cl:91-97) holds PRIVATE_STACK_SIZE = 100 two-operand entries (200 operand
+    slots here) and the reference never checks: a private stack within its limits gives the closed-form gradient,
+    one that outgrows them fails the evaluation with AD4CL_ERR_TAPE_OVERFLOW instead of pairing slots with the
+    wrong ids or sweeping past the private gradient."""
+    from ad4cl_b200 import host
+    n = 4099
+    x = np.linspace(0.5, 1.5, n)
+    xb = ctx.buffer(x)
+    theta = np.array([1.25, -0.75])
+
+    def run(links):
+        k = ctx.from_source(PRIVATE_OVERFLOW_SRC, "private_chain", "GSVDOii")
+        k.set_args(None, None, host.params(0, 2), xb, None, n, links)
+        k.configure(n, max_ops=8, max_slots=8)
+        try:
+            return k.eval(theta)
+        finally:
+            k.free()
+
+    links = 40                                   # 1 + 2 * 40 = 81 private operators: fits
+    f, g = run(links)
+    r = 0.5 ** links
+    v = theta[0] * x * r + theta[1] * 2.0 * (1.0 - r)
+    assert abs(f - v.sum()) <= 1e-12 * abs(v.sum())
+    assert abs(g[0] - (x * r).sum()) <= 1e-12 * abs((x * r).sum()) and abs(g[1] - n * 2.0 * (1.0 - r)) <= 1e-12 * n
+    with pytest.raises(host.Ad4clError) as e:
+        run(80)                                  # 161 operators / 241 operand slots: more than the stack's 100 two-operand entries
+    assert e.value.code == host.ERR_TAPE_OVERFLOW
