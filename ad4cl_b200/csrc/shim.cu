@@ -77,6 +77,7 @@ struct DriverApi {
     CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
             unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*cuFuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*cuGetErrorString)(CUresult, const char**) = nullptr;
     bool ok = false;
@@ -93,11 +94,12 @@ DriverApi& driver() {
     BIND(cuModuleGetFunction, "cuModuleGetFunction");
     BIND(cuLaunchKernel, "cuLaunchKernel");
     BIND(cuFuncSetAttribute, "cuFuncSetAttribute");
+    BIND(cuFuncGetAttribute, "cuFuncGetAttribute");
     BIND(cuOccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     BIND(cuGetErrorString, "cuGetErrorString");
 #undef BIND
     d.ok = d.cuModuleLoadData && d.cuModuleGetFunction && d.cuLaunchKernel && d.cuFuncSetAttribute
-            && d.cuOccupancyMaxActiveBlocksPerMultiprocessor;
+            && d.cuFuncGetAttribute && d.cuOccupancyMaxActiveBlocksPerMultiprocessor;
     return d;
 }
 
@@ -181,6 +183,14 @@ struct ad4cl_kernel {
     bool use_static = false;       /* prepare() selected one of them */
     CUmodule module = nullptr;     /* NVRTC kernel */
     CUfunction functions[2][3] = {};
+    /* JIT register tier: a kernel created from SOURCE can be rebuilt as a register-tier instance
+       (AD4CL_TAPE_STATIC) for the independents and integer arguments it is bound to; built lazily by
+       prepare(), kept while the key (independents, bindings, integer arguments) stays the same */
+    std::string source, options;
+    CUmodule static_module = nullptr;
+    CUfunction static_function = nullptr;
+    std::string static_key;        /* what static_module was built for ("" = never tried) */
+    bool static_usable = false;    /* ... and whether that build was scalarised (no local memory) */
     int recorder = 1;              /* the recorder (kernel) in use: 0 uniform-first, 1 lane */
     int acc = 0;                   /* the accumulator mode in use */
     CUfunction function = nullptr;
@@ -302,6 +312,69 @@ int occupancy(ad4cl_kernel* k, int block, size_t smem, int* blocks) {
     return AD4CL_OK;
 }
 
+struct StaticSpec {
+    int nparams = 0;
+    const std::vector<Arg>* args = nullptr;
+};
+/* Which integer arguments a register-tier instance is specialised on: the ones small enough to be the trip
+   count of a loop the 64-slot static tape can hold unrolled.  Large ones (the problem size of `id < size`)
+   stay run-time parameters -- as literals they buy nothing and were measured to cost registers. */
+inline bool static_freezes(int v) { return v >= 0 && v <= 64; }
+int compile_to_cubin(const char* source, const char* entry, const char* signature,
+        const char* options, int reference_quirks, std::vector<char>* cubin, const StaticSpec* stat = nullptr);
+
+/* JIT register tier: (re)build the register-tier instance of a kernel created from source for exactly these
+   independents / bindings / integer arguments, and report whether it can be used (it compiled and the
+   compiler scalarised the tape: no local memory).  Never fails the evaluation: a kernel that does not
+   qualify simply stays in the arena tiers. */
+bool jit_static_instance(ad4cl_kernel* k, int nparams, unsigned cap_slots) {
+    if (!k->module || k->source.empty()) return false;
+    if (nparams < 1 || nparams > 16 || cap_slots > 64) return false;   /* register accumulators / the 64-slot static tape */
+    if (k->functions[0][0] == nullptr) return false;                   /* work-group barriers: not a per-thread kernel */
+    std::string key = std::to_string(nparams) + "/" + std::to_string(k->cfg.reference_quirks);
+    int next = 0;
+    for (const Arg& a : k->args) {
+        if (a.kind == 'V') {
+            if (!a.set || a.first_id != next) return false;            /* independents bound in argument order */
+            next += a.count;
+            key += ":V" + std::to_string(a.first_id) + "+" + std::to_string(a.count);
+        } else if (a.kind == 'i') {
+            if (!a.set) return false;
+            key += static_freezes(a.ival) ? ":i" + std::to_string(a.ival) : std::string(":i*");
+        }
+    }
+    if (next != nparams) return false;
+    if (key == k->static_key) return k->static_usable;
+    if (k->static_module) driver().cuModuleUnload(k->static_module);
+    k->static_module = nullptr;
+    k->static_function = nullptr;
+    k->static_key = key;
+    k->static_usable = false;
+    StaticSpec spec;
+    spec.nparams = nparams;
+    spec.args = &k->args;
+    std::vector<char> bin;
+    if (compile_to_cubin(k->source.c_str(), k->name.c_str(), k->signature.c_str(), k->options.empty() ? nullptr : k->options.c_str(),
+            k->cfg.reference_quirks, &bin, &spec) != AD4CL_OK)
+        return false;   /* e.g. the kernel indexes its independents in a way the local copies cannot serve */
+    if (driver().cuModuleLoadData(&k->static_module, bin.data()) != CUDA_SUCCESS) {
+        k->static_module = nullptr;
+        return false;
+    }
+    const std::string fn = k->name + "__entry_s";
+    int local_bytes = 1;
+    if (driver().cuModuleGetFunction(&k->static_function, k->static_module, fn.c_str()) != CUDA_SUCCESS
+            || driver().cuFuncGetAttribute(&local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, k->static_function) != CUDA_SUCCESS
+            || local_bytes != 0) {
+        driver().cuModuleUnload(k->static_module);
+        k->static_module = nullptr;
+        k->static_function = nullptr;
+        return false;   /* the tape did not become registers: the arena tiers are the faster home */
+    }
+    k->static_usable = true;
+    return true;
+}
+
 /* size every device resource for `nparams` independents */
 int prepare(ad4cl_kernel* k, int nparams) {
     if (k->ready && k->nparams == nparams) return AD4CL_OK;
@@ -347,6 +420,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
        scalarised (no local memory).  Otherwise AUTO = the HBM arena, which stays L2 resident for short
        tapes; the shared-memory tier is only ever chosen explicitly. */
     const ad4cl_static_row* srow = nullptr;
+    bool jstat = false;
     if (tier == AD4CL_TAPE_AUTO || tier == AD4CL_TAPE_REGISTER) {
         for (const ad4cl_static_row* r : k->static_rows) {
             if (r->nparams != nparams) continue;
@@ -375,19 +449,27 @@ int prepare(ad4cl_kernel* k, int nparams) {
                 break;
             }
         }
-        if (tier == AD4CL_TAPE_REGISTER && !srow)
+        /* a kernel created from source: build its register-tier instance now (AUTO under the same conditions
+           as for the built-in instances) */
+        if (!srow && k->module && g1 == 1 && block <= AD4CL_STATIC_MAX_BLOCK
+                && (tier == AD4CL_TAPE_REGISTER || (c.window == 0 && c.far_plane != 0
+                        && (c.acc_mode == AD4CL_ACC_AUTO || c.acc_mode == AD4CL_ACC_THREAD))))
+            jstat = jit_static_instance(k, nparams, cap_slots);
+        if (tier == AD4CL_TAPE_REGISTER && !srow && !jstat)
             return fail(AD4CL_ERR_INVALID, "kernel %s has no register-tier instance for %d independents with these "
-                    "arguments (built-in instances: linreg2_g / linreg2_p with 2, regression_* with 10)", k->name.c_str(), nparams);
-        tier = srow ? AD4CL_TAPE_REGISTER : AD4CL_TAPE_HBM;
+                    "arguments (built-in instances: linreg2_g / linreg2_p with 2, regression_* with 10; kernels created "
+                    "from source: 1-D, <= 16 independents bound in argument order, max_slots <= 64, no barrier, and a "
+                    "tape the compiler can scalarise)", k->name.c_str(), nparams);
+        tier = (srow || jstat) ? AD4CL_TAPE_REGISTER : AD4CL_TAPE_HBM;
     }
-    k->use_static = srow != nullptr;
-    if (srow) {
-        acc = AD4CL_ACC_THREAD; /* per-thread REGISTER accumulators */
-        k->entry = srow->entry;
-    }
-    const bool fused = srow != nullptr || (acc != AD4CL_ACC_GLOBAL && nparams <= ad4cl::kInKernelPackMax);
+    const bool stat = srow != nullptr || jstat;
+    k->use_static = stat;
+    if (stat) acc = AD4CL_ACC_THREAD; /* per-thread REGISTER accumulators */
+    if (srow) k->entry = srow->entry;
+    if (jstat) k->function = k->static_function;
+    const bool fused = stat || (acc != AD4CL_ACC_GLOBAL && nparams <= ad4cl::kInKernelPackMax);
 
-    const size_t smem = srow ? sizeof (double) * (size_t) (block / 32) * (nparams + 3)
+    const size_t smem = stat ? sizeof (double) * (size_t) (block / 32) * (nparams + 3)
             : ad4cl::entry_smem_bytes(block, nparams, window, acc, tier == AD4CL_TAPE_SHARED, cap_slots, far);
     if (smem > k->ctx->prop.sharedMemPerBlockOptin)
         return fail(AD4CL_ERR_INVALID, "kernel %s needs %zu B of shared memory per block (limit %zu): "
@@ -396,7 +478,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
     int per_sm = 0;
     int rc = occupancy(k, block, smem, &per_sm);
     if (rc != AD4CL_OK) return rc;
-    if (!srow) { /* the other recorder's kernel may be launched too (AUTO times both): same opt-in, the smaller occupancy */
+    if (!stat) { /* the other recorder's kernel may be launched too (AUTO times both): same opt-in, the smaller occupancy */
         const int other = 1 - k->recorder;
         if (k->module ? k->functions[other][acc] != nullptr : k->entries[other][acc] != nullptr) {
             const void* e0 = k->entry;
@@ -423,7 +505,7 @@ int prepare(ad4cl_kernel* k, int nparams) {
        lock step (LaunchInfo::lockstep) all resident warps then walk the same stretch of a long objective
        together, which is what a body larger than the instruction caches wants (profiles/README.md).
        Only when the caller left the work-group size open, for 1-D arena kernels. */
-    if (!srow && tier == AD4CL_TAPE_HBM && c.local_size[0] <= 0 && g1 == 1 && c.blocks_per_sm <= 0
+    if (!stat && tier == AD4CL_TAPE_HBM && c.local_size[0] <= 0 && g1 == 1 && c.blocks_per_sm <= 0
             && AD4CL_MAX_BLOCK > block && c.global_size[0] >= (long long) AD4CL_MAX_BLOCK * k->ctx->prop.multiProcessorCount) {
         const int b2 = AD4CL_MAX_BLOCK;
         const size_t smem2 = ad4cl::entry_smem_bytes(b2, nparams, window, acc, false, cap_slots, far);
@@ -498,9 +580,9 @@ int prepare(ad4cl_kernel* k, int nparams) {
     L.tape_in_smem = tier == AD4CL_TAPE_SHARED ? 1 : 0;
     L.sweep_prefetch = c.sweep_prefetch == AD4CL_PREFETCH_ON ? 1 : 0;
     /* AUTO: decided by autotune_recorder on the first gradient evaluation (the register tier has no choice to make) */
-    k->tune_pending = !srow && (c.recorder == AD4CL_RECORDER_AUTO || c.sweep_prefetch == AD4CL_PREFETCH_AUTO
+    k->tune_pending = !stat && (c.recorder == AD4CL_RECORDER_AUTO || c.sweep_prefetch == AD4CL_PREFETCH_AUTO
                                 || c.lockstep == AD4CL_LOCKSTEP_AUTO || k->nshapes > 1);
-    k->stats.recorder = k->tune_pending && c.recorder == AD4CL_RECORDER_AUTO ? -1 : (srow ? -1 : k->recorder);
+    k->stats.recorder = k->tune_pending && c.recorder == AD4CL_RECORDER_AUTO ? -1 : (stat ? -1 : k->recorder);
     k->stats.sweep_prefetch = k->tune_pending && c.sweep_prefetch == AD4CL_PREFETCH_AUTO ? -1 : L.sweep_prefetch;
     L.cap_slots = cap_slots;
     L.arena = k->arena;
@@ -931,9 +1013,13 @@ int ad4cl_cuda_kernel_builtin(ad4cl_context* ctx, const char* name, int referenc
     return fail(AD4CL_ERR_INVALID, "no built-in kernel named '%s'", name);
 }
 
-/* OpenCL prelude + user text + generated entry -> sm_100a cubin (no device needed) */
-static int compile_to_cubin(const char* source, const char* entry, const char* signature,
-        const char* options, int reference_quirks, std::vector<char>* cubin) {
+extern "C++" {
+namespace {
+/* OpenCL prelude + user text + generated entry -> sm_100a cubin (no device needed).  With `stat` the
+   generated entry is the register-tier one: the independents are local copies `th` with literal ids and the
+   integer arguments are literals (they bound the kernel's loops, which must unroll for the tape to scalarise). */
+int compile_to_cubin(const char* source, const char* entry, const char* signature,
+        const char* options, int reference_quirks, std::vector<char>* cubin, const StaticSpec* stat) {
     if (!source || !entry) return fail(AD4CL_ERR_INVALID, "NULL argument");
     if (!signature_ok(signature)) return fail(AD4CL_ERR_INVALID, "bad signature '%s' (letters GSOVDIid, exactly one O)", signature ? signature : "");
     NvrtcApi& n = nvrtc();
@@ -944,7 +1030,9 @@ static int compile_to_cubin(const char* source, const char* entry, const char* s
         char nm[32];
         snprintf(nm, sizeof nm, "a%zu", i);
         const char c = signature[i];
-        const char* passed = c == 'G' ? "gs" : c == 'S' ? "gradient_stack" : c == 'O' ? "out" : nm;
+        std::string passed = c == 'G' ? "gs" : c == 'S' ? "gradient_stack" : c == 'O' ? "out" : nm;
+        if (stat && c == 'V') passed = "th + " + std::to_string((*stat->args)[i].first_id);
+        if (stat && c == 'i' && static_freezes((*stat->args)[i].ival)) passed = "(" + std::to_string((*stat->args)[i].ival) + ")";
         if (!call.empty()) call += ", ";
         call += passed;
         const char* type = c == 'V' ? "struct ad_variable* " : c == 'D' ? "double* " : c == 'I' ? "int* "
@@ -957,7 +1045,7 @@ static int compile_to_cubin(const char* source, const char* entry, const char* s
     }
     std::string tu = "#include \"ad4cl_opencl_compat.cuh\"\n#line 1 \"user_kernel.cl\"\n";
     tu += source;
-    tu += "\n#line 1 \"ad4cl_generated_entry\"\nAD4CL_OBJECTIVE_ENTRY(";
+    tu += stat ? "\n#line 1 \"ad4cl_generated_entry\"\nAD4CL_STATIC_ENTRY(" : "\n#line 1 \"ad4cl_generated_entry\"\nAD4CL_OBJECTIVE_ENTRY(";
     tu += entry;
     tu += ", (" + params + "), (" + call + "))\n";
 
@@ -967,6 +1055,10 @@ static int compile_to_cubin(const char* source, const char* entry, const char* s
     if (rc != 0) return fail(AD4CL_ERR_COMPILE, "nvrtcCreateProgram failed: %d", rc);
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
         std::string("-DAD4CL_REFERENCE_QUIRKS=") + (reference_quirks ? "1" : "0")};
+    if (stat) {
+        opts.push_back("-DAD4CL_TAPE_STATIC=1");
+        opts.push_back("-DAD4CL_P=" + std::to_string(stat->nparams));
+    }
     /* a kernel that synchronises its work-group cannot be re-run by a single warp after a failed optimistic
        recording attempt (ad4cl_entry.cuh): build it with the general recorder only */
     if (strstr(source, "barrier") != nullptr || strstr(source, "__syncthreads") != nullptr || strstr(source, "__local") != nullptr
@@ -1000,6 +1092,8 @@ static int compile_to_cubin(const char* source, const char* entry, const char* s
     n.DestroyProgram(&prog);
     return AD4CL_OK;
 }
+} // namespace
+} // extern "C++"
 
 int ad4cl_cuda_compile(const char* source, const char* entry, const char* signature, const char* options,
         int reference_quirks, void** cubin, size_t* cubin_bytes) {
@@ -1053,7 +1147,12 @@ int ad4cl_cuda_kernel_from_source(ad4cl_context* ctx, const char* source, const 
     std::vector<char> bin;
     int rc = compile_to_cubin(source, entry, signature, options, reference_quirks, &bin);
     if (rc != AD4CL_OK) return rc;
-    return ad4cl_cuda_kernel_from_cubin(ctx, bin.data(), bin.size(), entry, signature, reference_quirks, out);
+    rc = ad4cl_cuda_kernel_from_cubin(ctx, bin.data(), bin.size(), entry, signature, reference_quirks, out);
+    if (rc == AD4CL_OK) { /* kept for the register-tier instance prepare() may build (jit_static_instance) */
+        (*out)->source = source;
+        (*out)->options = options ? options : "";
+    }
+    return rc;
 }
 
 int ad4cl_cuda_kernel_free(ad4cl_kernel* k) {
@@ -1064,6 +1163,7 @@ int ad4cl_cuda_kernel_free(ad4cl_kernel* k) {
     if (k->ev0) cudaEventDestroy(k->ev0);
     if (k->ev1) cudaEventDestroy(k->ev1);
     for (auto& e : k->prof_events) cudaEventDestroy(e);
+    if (k->static_module && driver().cuModuleUnload) driver().cuModuleUnload(k->static_module);
     if (k->module && driver().cuModuleUnload) driver().cuModuleUnload(k->module);
     delete k;
     return AD4CL_OK;
@@ -1097,6 +1197,7 @@ int ad4cl_cuda_kernel_set_arg_int(ad4cl_kernel* k, int index, int value) {
     Arg* a = nullptr;
     int rc = arg_at(k, index, "i", &a);
     if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
+    if (k->use_static && (!a->set || a->ival != value)) k->ready = false;   /* register-tier instances freeze their small integer arguments */
     a->ival = value;
     a->set = true;
     k->drop_graphs();
@@ -1118,6 +1219,7 @@ int ad4cl_cuda_kernel_set_arg_params(ad4cl_kernel* k, int index, int first_id, i
     int rc = arg_at(k, index, "V", &a);
     if (rc != AD4CL_OK) return rc > 0 ? AD4CL_OK : rc;
     if (first_id < 0 || count < 1) return fail(AD4CL_ERR_INVALID, "bad independent range [%d,+%d)", first_id, count);
+    if (k->use_static && (a->first_id != first_id || a->count != count)) k->ready = false;
     a->first_id = first_id;
     a->count = count;
     a->buf = nullptr;

@@ -61,7 +61,7 @@ def test_jit_kernel_matches_builtin_and_oracle(ctx, oracle_api):
     kj = ctx.from_source(text, "regression_logistic", "GSVDDOiii")
     d0, d1 = ctx.buffer(w.d0), ctx.buffer(w.d1)
     kj.set_args(None, None, host.params(0, w.nparams), d0, d1, None, w.size, w.i0, w.i1)
-    kj.configure(w.size, max_ops=w.max_ops, max_slots=w.max_slots)
+    kj.configure(w.size, max_ops=w.max_ops, max_slots=w.max_slots, tape="hbm")
     fj, gj = kj.eval(w.theta)
     kj.free()
     assert rel_err(fj, ref["f"]) <= RTOL and rel_err(gj, ref["grad"]) <= RTOL
@@ -214,3 +214,52 @@ def test_private_stack_overflow_is_reported_not_clipped(ctx):
     with pytest.raises(host.Ad4clError) as e:
         run(80)                                  # 161 operators / 241 operand slots: more than the stack's 100 two-operand entries
     assert e.value.code == host.ERR_TAPE_OVERFLOW
+
+
+@pytest.mark.gpu
+def test_kernels_from_source_get_a_register_tier_instance(ctx, oracle_api):
+    """AD4CL_TAPE_AUTO for a kernel created from SOURCE: when it is bound (independents in argument order, integer
+    arguments set) the library rebuilds it as a register-tier instance -- local copies of the independents with
+    literal ids, small integer arguments as literals so the loops they bound unroll -- and uses it if the compiler
+    scalarised the tape (no local memory).  Same bits as the ahead-of-time register-tier build of the same text;
+    a tape that cannot be a compile-time shape stays in the arena, and asking for the register tier then fails."""
+    from ad4cl_b200 import host
+    text = open(os.path.join(REPO, "ad4cl_b200", "kernels", "objectives.cl")).read()
+    for name, n in (("regression_logistic", 30011), ("linreg2_simple", 50021)):
+        w = W.describe(name, n)
+        kb = W.bind(ctx, w)
+        fb, gb = kb.eval(w.theta)
+        assert kb.stats()["tape_tier"] == "register"
+        kb.free()
+        d0, d1 = ctx.buffer(w.d0), ctx.buffer(w.d1)
+        if w.linreg2:
+            kj = ctx.from_source(text, w.kernel, "GSVVDDOi")
+            kj.set_args(None, None, host.params(0), host.params(1), d0, d1, None, w.size)
+        else:
+            kj = ctx.from_source(text, w.kernel, "GSVDDOiii")
+            kj.set_args(None, None, host.params(0, w.nparams), d0, d1, None, w.size, w.i0, w.i1)
+        kj.configure(w.size, max_ops=w.max_ops, max_slots=w.max_slots, epilogue=w.epilogue, epilogue_n=w.epilogue_n)
+        fj, gj = kj.eval(w.theta)
+        st = kj.stats()
+        fj2, gj2 = kj.eval(w.theta)
+        launches = kj.launches_per_eval
+        kj.free()
+        assert st["tape_tier"] == "register" and launches == 1
+        assert fj == fb and np.array_equal(gj, gb), "JIT and ahead-of-time register-tier builds of the same text disagree"
+        assert fj2 == fj and np.array_equal(gj2, gj)
+        ref = oracle_api.best(False).eval_objective(w.kernel, w.theta, w.d0, w.d1, w.size, w.i0, w.i1,
+                                                   epilogue=1 if w.epilogue == "half_n_log" else 0, ops_per_item=w.max_ops)
+        assert rel_err(fj, ref["f"]) <= RTOL and rel_err(gj, ref["grad"]) <= RTOL
+    # 200 steps = 801 slots: not a register-tier tape
+    w = W.describe("tape_stress", 5003, steps=200)
+    kj = ctx.from_source(text, "tape_stress", "GSVDDOiii")
+    d0 = ctx.buffer(w.d0)
+    kj.set_args(None, None, host.params(0, w.nparams), d0, None, None, w.size, w.i0, w.i1)
+    kj.configure(w.size, max_ops=w.max_ops, max_slots=w.max_slots)
+    f, g = kj.eval(w.theta)
+    assert kj.stats()["tape_tier"] == "hbm"
+    kj.configure(w.size, max_ops=w.max_ops, max_slots=w.max_slots, tape="register")
+    with pytest.raises(host.Ad4clError) as e:
+        kj.eval(w.theta)
+    assert e.value.code == host.ERR_INVALID
+    kj.free()
