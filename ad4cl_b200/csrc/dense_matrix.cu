@@ -35,24 +35,26 @@ constexpr int PAD = 4; /* row stride 68: the DMMA fragment reads (4 k-rows x 4..
    HBM/L2 latency overlaps it), then registers -> shared after the arithmetic.  Tiles are kept k-major
    in shared memory: As[k][m], Bs[k][n].  The contiguous direction of the global read follows the
    operand's storage, so the loads are coalesced for op = N and op = T alike. */
-template <bool TA, bool TB, int NT>
+template <bool TA, bool TB, int NT, bool ONES_A = false, bool ONES_B = false>
 struct TileStage {
     static constexpr int EA = BM * BK / NT, EB = BK * BN / NT;
     double a[EA], b[EB];
 
+    /* ONES_A / ONES_B: that operand is the all-ones matrix (G = 1, the reference's objective sum C):
+       nothing is read for it */
     __device__ __forceinline__ void fetch(const double* __restrict__ A, const double* __restrict__ B, int n,
             int m0, int n0, int k0, int tid) {
 #pragma unroll
         for (int i = 0; i < EA; i++) {
             const int e = tid + i * NT;
             const int m = TA ? e % BM : e / BK, k = TA ? e / BM : e % BK;
-            a[i] = at<TA>(A, n, m0 + m, k0 + k);
+            a[i] = ONES_A ? 1.0 : at<TA>(A, n, m0 + m, k0 + k);
         }
 #pragma unroll
         for (int i = 0; i < EB; i++) {
             const int e = tid + i * NT;
             const int k = TB ? e % BK : e / BN, c = TB ? e / BK : e % BN;
-            b[i] = at<TB>(B, n, k0 + k, n0 + c);
+            b[i] = ONES_B ? 1.0 : at<TB>(B, n, k0 + k, n0 + c);
         }
     }
 
@@ -199,6 +201,122 @@ __global__ void __launch_bounds__(128) dgemm_mma(const double* __restrict__ A, c
     }
 }
 
+/* ---------------------------------------------------------------- variant 2: all three products, ONE launch
+ * C = A B, dA = G B^T and dB = A^T G are 3 (n/64)^2 independent 64x64 tiles.  A persistent grid (as many CTAs
+ * as are resident) draws tiles from one atomic counter, longest-first order being irrelevant (all tiles cost the
+ * same): the last wave is at most one tile per CTA instead of the 1.7-wave grid of one launch per product, and
+ * two launches, the all-ones fill of G and the separate sum kernel disappear -- the CTA that finishes the last
+ * tile adds the per-tile sums of C in tile order.  The tile arithmetic is dgemm_mma's. */
+struct Gemm3 {
+    const double* A; const double* B; const double* G;   /* G == nullptr: all ones */
+    double* C; double* dA; double* dB;                    /* each may be nullptr: product skipped */
+    double* tile_sums;                                    /* (n/64)^2 doubles */
+    double* sum_out;                                      /* may be nullptr */
+    unsigned* counters;                                   /* [0] next tile, [1] tiles finished; both zero at launch, reset by the last CTA */
+    int n;
+};
+
+template <bool TA, bool TB, bool ONES_A, bool ONES_B>
+__device__ __forceinline__ double gemm_tile_mma(const double* __restrict__ A, const double* __restrict__ B,
+        double* __restrict__ C, int n, int m0, int n0, double (*As)[BK][BM + PAD], double (*Bs)[BK][BN + PAD]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int g = lane >> 2, q = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    TileStage<TA, TB, 128, ONES_A, ONES_B> stage;
+    stage.fetch(A, B, n, m0, n0, 0, tid);
+    __syncthreads();                       /* the previous tile's readers are done with the buffers */
+    stage.store(As[0], Bs[0], tid);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < n; k0 += BK) {
+        const bool more = k0 + BK < n;
+        if (more) stage.fetch(A, B, n, m0, n0, k0 + BK, tid);
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[buf][k4 + q][wm + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[buf][k4 + q][wn + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (more) stage.store(As[buf ^ 1], Bs[buf ^ 1], tid);
+        __syncthreads();
+        buf ^= 1;
+    }
+    double local = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double* p = C + (size_t) (m0 + wm + i * 8 + g) * n + n0 + wn + j * 8 + 2 * q;
+            *reinterpret_cast<double2*> (p) = make_double2(acc[i][j][0], acc[i][j][1]);
+            local += acc[i][j][0] + acc[i][j][1];
+        }
+    return local;
+}
+
+__global__ void __launch_bounds__(128, 4) dgemm3_persistent(const Gemm3 P) {
+    __shared__ double As[2][BK][BM + PAD];
+    __shared__ double Bs[2][BK][BN + PAD];
+    __shared__ double red[128];
+    __shared__ unsigned next_tile, finished;
+    const int tid = threadIdx.x;
+    const int tn = P.n / BN, per = tn * tn;
+    /* products in a fixed order; a skipped product contributes no tiles */
+    const int base1 = P.C ? per : 0, base2 = base1 + (P.dA ? per : 0), total = base2 + (P.dB ? per : 0);
+    for (;;) {
+        if (tid == 0) next_tile = atomicAdd(&P.counters[0], 1u);
+        __syncthreads();
+        const unsigned t = next_tile;
+        if (t >= (unsigned) total) break;
+        const int which = (int) t < base1 ? 0 : ((int) t < base2 ? 1 : 2);
+        const int local_t = (int) t - (which == 0 ? 0 : (which == 1 ? base1 : base2));
+        const int m0 = (local_t / tn) * BM, n0 = (local_t % tn) * BN;
+        double s;
+        if (which == 0) s = gemm_tile_mma<false, false, false, false>(P.A, P.B, P.C, P.n, m0, n0, As, Bs);
+        else if (which == 1) s = P.G ? gemm_tile_mma<false, true, false, false>(P.G, P.B, P.dA, P.n, m0, n0, As, Bs)
+                                     : gemm_tile_mma<false, true, true, false>(P.G, P.B, P.dA, P.n, m0, n0, As, Bs);
+        else s = P.G ? gemm_tile_mma<true, false, false, false>(P.A, P.G, P.dB, P.n, m0, n0, As, Bs)
+                     : gemm_tile_mma<true, false, false, true>(P.A, P.G, P.dB, P.n, m0, n0, As, Bs);
+        if (which == 0 && P.sum_out) { /* fixed-order sum of this tile of C */
+            red[tid] = s;
+            __syncthreads();
+            if (tid == 0) {
+                double v = 0.0;
+                for (int i = 0; i < 128; i++) v += red[i];
+                P.tile_sums[local_t] = v;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) finished = atomicAdd(&P.counters[1], 1u);
+        __syncthreads();
+        if (finished == (unsigned) total - 1) { /* the last tile of the launch: the objective, and leave the counters ready */
+            __threadfence();
+            if (P.sum_out && P.C && tid == 0) {
+                double v = 0.0;
+                for (int i = 0; i < per; i++) v += reinterpret_cast<volatile double*> (P.tile_sums)[i];
+                *P.sum_out = v;
+            }
+            if (tid == 0) P.counters[1] = 0u;
+        }
+    }
+    /* every CTA leaves through one more draw (>= total); the one that sees the last of them resets the draw counter */
+    if (tid == 0) {
+        const unsigned draws = total + gridDim.x;
+        if (next_tile == draws - 1) P.counters[0] = 0u;
+    }
+}
+
 __global__ void fill_ones(double* p, size_t n) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 1.0;
@@ -250,13 +368,45 @@ int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, cons
         const double* G_dev, double* C_dev, double* dA_dev, double* dB_dev, double* sum_dev, double* workspace_dev) {
     if (!ctx || !A_dev || !B_dev || !workspace_dev) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "NULL argument");
     if (n <= 0 || n % 64 != 0) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "dense path needs n to be a multiple of 64");
-    if (variant != 0 && variant != 1) return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "variant must be 0 (DFMA) or 1 (DMMA)");
+    if (variant < 0 || variant > 2)
+        return ad4cl_cuda_set_error_(AD4CL_ERR_INVALID, "variant must be 0 (DFMA), 1 (DMMA, one launch per product) or 2 (DMMA, all products in one persistent launch)");
     cudaStream_t st = (cudaStream_t) ad4cl_cuda_stream(ctx);
     const size_t nn = (size_t) n * n;
     double* scratch = workspace_dev;          /* C when the caller does not want it, or G = 1 */
     double* sums = workspace_dev + nn;
     const int nblocks = (n / 64) * (n / 64);
     cudaError_t e = cudaSuccess;
+    if (variant == 2) {
+        static unsigned* counters[64] = {};   /* per device, zero between launches (the kernel resets them) */
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static int resident = 0;
+        if (!counters[dev & 63]) {
+            if (cudaMalloc(&counters[dev & 63], 2 * sizeof (unsigned)) != cudaSuccess
+                    || cudaMemset(counters[dev & 63], 0, 2 * sizeof (unsigned)) != cudaSuccess)
+                return ad4cl_cuda_set_error_(AD4CL_ERR_NOMEM, "dense path: counter allocation failed");
+        }
+        if (!resident) {
+            int per_sm = 0, sms = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dgemm3_persistent, 128, 0);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            resident = per_sm * sms;
+        }
+        Gemm3 P;
+        P.A = A_dev; P.B = B_dev; P.G = G_dev;
+        P.C = (C_dev || sum_dev) ? (C_dev ? C_dev : scratch) : nullptr;
+        P.dA = dA_dev; P.dB = dB_dev;
+        P.tile_sums = sums; P.sum_out = sum_dev; P.counters = counters[dev & 63]; P.n = n;
+        const int total = ((P.C ? 1 : 0) + (P.dA ? 1 : 0) + (P.dB ? 1 : 0)) * nblocks;
+        if (total > 0) dgemm3_persistent<<<resident < total ? resident : total, 128, 0, st>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            char msg[256];
+            snprintf(msg, sizeof msg, "dense matrix product failed: %s", cudaGetErrorString(e));
+            return ad4cl_cuda_set_error_(AD4CL_ERR_CUDA, msg);
+        }
+        return AD4CL_OK;
+    }
     if (C_dev || sum_dev) {
         double* Cout = C_dev ? C_dev : scratch;
         e = gemm<false, false>(variant, A_dev, B_dev, Cout, n, sum_dev ? sums : nullptr, st);

@@ -463,9 +463,10 @@ class Context:
 
     def matrix_product_dense(self, n: int, A: Buffer, B: Buffer, *, G: Buffer | None = None, C: Buffer | None = None,
                              dA: Buffer | None = None, dB: Buffer | None = None, total: Buffer | None = None,
-                             workspace: Buffer | None = None, variant: int = 1) -> None:
+                             workspace: Buffer | None = None, variant: int = 2) -> None:
         """config 2 without a tape: C = A B, sum C, dL/dA = G B^T, dL/dB = A^T G (asynchronous).
-        variant 1 = fp64 tensor-core DMMA (default: measured 2.3x faster than variant 0, DFMA)."""
+        variant 2 (default) = fp64 tensor-core DMMA, all products in ONE persistent launch; 1 = DMMA, one launch per
+        product; 0 = CUDA-core DFMA (2.3x slower than 1)."""
         p = lambda b: None if b is None else b.device_ptr  # noqa: E731
         _check(lib.ad4cl_cuda_matrix_product_dense(self._h, variant, n, p(A), p(B), p(G), p(C), p(dA), p(dB),
                                                    p(total), p(workspace)))

@@ -304,7 +304,8 @@ int ad4cl_cuda_minimize_lbfgs_device(ad4cl_kernel* kernel, double* theta, int nu
  * L = sum_{j,i} G[j,i] C[j,i] as two more products, dL/dA = G*B^T and dL/dB = A^T*G.
  * Row-major n x n doubles in device memory, n a multiple of 64.  G_dev NULL means G = 1 (the
  * reference's objective).  C_dev, dA_dev, dB_dev, sum_dev may each be NULL to skip that output.
- * workspace_dev: n*n + (n/64)^2 doubles.  variant 0: CUDA-core DFMA, 1: fp64 tensor-core DMMA.
+ * workspace_dev: n*n + (n/64)^2 doubles.  variant 0: CUDA-core DFMA, 1: fp64 tensor-core DMMA (one launch per
+ * product), 2: DMMA, every requested product in ONE persistent launch (tiles drawn from a counter; G = NULL costs no fill).
  * Asynchronous on the context's stream.
  */
 int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, const double* A_dev,

@@ -21,7 +21,7 @@ def run_dense(ctx, n, A, B, G=None, variant=0):
     return out
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["dfma", "dmma"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["dfma", "dmma", "dmma-one-launch"])
 @pytest.mark.parametrize("n", [64, 256])
 def test_dense_matches_numpy_and_oracle(ctx, oracle_api, n, variant):
     A, B = synth.msvcrt_rand_matrices(n)
@@ -40,7 +40,7 @@ def test_dense_matches_numpy_and_oracle(ctx, oracle_api, n, variant):
         assert np.max(np.abs(C.ravel() - ref["C"])) <= 1e-12 * np.abs(ref["C"]).max()
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["dfma", "dmma"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["dfma", "dmma", "dmma-one-launch"])
 def test_dense_with_general_seed(ctx, variant):
     n = 128
     A, B = synth.msvcrt_rand_matrices(n)

@@ -138,7 +138,7 @@ def test_matrix_1024_tape_and_dense_paths(ctx):
     bA, bB = ctx.buffer(A), ctx.buffer(B)
     bC, bdA, bdB = (ctx.buffer(nbytes=8 * n * n) for _ in range(3))
     tot, ws = ctx.buffer(nbytes=8), ctx.buffer(nbytes=8 * (2 * n * n + 4096))
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.matrix_product_dense(n, bA, bB, C=bC, dA=bdA, dB=bdB, total=tot, workspace=ws, variant=variant)
         C = bC.download().reshape(n, n)
         assert np.max(np.abs(C - Am @ Bm)) <= 1e-12 * np.abs(Am @ Bm).max()
