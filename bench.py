@@ -435,6 +435,8 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--prefetch", default="auto", choices=["auto", "off", "on"],
                     help="sweep L2 prefetch (auto: the library times both on the first evaluation)")
+    ap.add_argument("--no-l2-flush", action="store_true",
+                    help="diagnostic only (never a bench value): skip the 256 MiB L2 flush before each timed step")
     ap.add_argument("--lockstep", default="auto", choices=["auto", "on", "off"],
                     help="work-groups in lock step (one barrier per work-item): keeps the warps' instruction fetches together")
     ap.add_argument("--recorder", default="auto", choices=["auto", "uniform", "lane"],
@@ -552,7 +554,8 @@ def main():
     barrier()
     sampler.start()
     for i in range(K):
-        flush.fill_(i & 0xFF)
+        if not args.no_l2_flush:
+            flush.fill_(i & 0xFF)
         starts[i].record(stream)
         step_device()
         ends[i].record(stream)
@@ -673,7 +676,7 @@ def main():
             # identical in both arms (the driver compares them); the launch shape of this arm is in `launch`
             "config": config,
             "launch": dict(ad_ops_per_eval=int(st_result[P + 1]), operand_slots_per_eval=int(st_result[P + 2]),
-                           l2="flushed (256 MiB write) before every timed step", grid=stats["grid"],
+                           l2="NOT flushed (diagnostic run, not a bench value)" if args.no_l2_flush else "flushed (256 MiB write) before every timed step", grid=stats["grid"],
                            block=stats["block"], smem_bytes=stats["smem_bytes"], arena_bytes=stats["arena_bytes"],
                            tape_tier=stats["tape_tier"], acc_mode=args.acc, launches_per_eval=k.launches_per_eval,
                            recorder=stats["recorder"], sweep_prefetch=stats["sweep_prefetch"], lockstep=stats["lockstep"],
