@@ -295,14 +295,15 @@ ad4cl_kernel* new_kernel(ad4cl_context* ctx, const char* name, const char* sig) 
 }
 
 int occupancy(ad4cl_kernel* k, int block, size_t smem, int* blocks) {
-    /* the entry's static shared memory (~3 KB) counts against the 48 KB default as well: opt in early */
+    /* the entry's static shared memory (7 KB, plus the user kernel's own __local arrays) counts against the 48 KB
+       default as well: opt in early */
     if (!k->module) {
-        if (smem > 36 * 1024)
+        if (smem > 8 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(k->entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k->entry, block, smem));
     } else {
         DriverApi& d = driver();
-        if (smem > 36 * 1024) {
+        if (smem > 8 * 1024) {
             CUresult r = d.cuFuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) smem);
             if (r != CUDA_SUCCESS) return fail(AD4CL_ERR_CUDA, "cuFuncSetAttribute(smem=%zu) failed: %d", smem, (int) r);
         }
