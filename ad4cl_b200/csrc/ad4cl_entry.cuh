@@ -472,7 +472,8 @@ __device__ __forceinline__ void run_objective(const LaunchInfo& L, Body&& body) 
             if (same && tape_classify_uniform(tape_hdr(tape), tape.far_adj, tape.next_id - tape.first_temp, tape.first_temp, tape.wm1)) same = 0;
             if (same) {
                 opt_fails = 0;
-                tape_sweep_uniform<MODE>(tape, outv.id, seed, T, pend);
+                if (L.sweep_prefetch) tape_sweep_uniform<MODE, true>(tape, outv.id, seed, T, pend);
+                else tape_sweep_uniform<MODE, false>(tape, outv.id, seed, T, pend);
             } else {
                 opt_fails++;
                 general = true;

@@ -788,7 +788,7 @@ struct UniformSweep {
     }
 };
 
-template <int MODE>
+template <int MODE, bool PREFETCH>
 __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, double seed, const SweepTarget& T, PendingParam& pend) {
     int rows = sweep_seed<MODE>(t.next_id - t.first_temp, t.first_temp, t.wm1, out_id, seed, T);
     if (rows <= 0) return;
@@ -819,7 +819,15 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, do
     S.load_words(b, wordA);
     S.load_cells(offA, dxA);
     S.load_offsets(b - 1, offB);
+    /* `prefetch`: a cell's address does not depend on its header (cell 2 + s belongs to row s), so lanes 0..7 can
+       pull the 1 KB of cells of the batch THREE below the one in use into L2 long before its headers are read --
+       for tapes longer than L2, where the one batch of register look-ahead is shorter than an HBM round trip.
+       Rows whose partial is +-1 have no cell: their lines are fetched for nothing, which a bandwidth-bound sweep
+       would pay for and a latency-bound one does not (the tuner measures). */
+    const char* pf_base = cells - (size_t) (threadIdx.x & 31) * 8 + (size_t) kUnitCells * kCellRowBytes + (size_t) (threadIdx.x & 31) * 128;
+    const bool pf_lane = PREFETCH && (threadIdx.x & 31) < 8;   /* a template parameter: the sweep without prefetch carries none of this */
     for (;;) {
+        if (PREFETCH && pf_lane && b >= 3) asm volatile("prefetch.global.L2 [%0];" : : "l"(pf_base + (size_t) (b - 3) * (4 * kCellRowBytes)));
         /* A holds batch b; B becomes batch b-1 */
         S.load_cells(offB, dxB);
         S.load_words(b - 1, wordB);
@@ -827,6 +835,7 @@ __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, do
         S.batch(b, T.ring + rb, wordA, dxA);
         rb = (rb - 32u) & wmask8;
         if (--b < 0) break;
+        if (PREFETCH && pf_lane && b >= 3) asm volatile("prefetch.global.L2 [%0];" : : "l"(pf_base + (size_t) (b - 3) * (4 * kCellRowBytes)));
         /* B holds batch b; A becomes batch b-1 */
         S.load_cells(offA, dxA);
         S.load_words(b - 1, wordA);

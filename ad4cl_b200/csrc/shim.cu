@@ -773,11 +773,10 @@ int autotune_recorder(ad4cl_kernel* k, const double* theta_dev) {
         if (c.recorder != AD4CL_RECORDER_AUTO && (c.recorder == AD4CL_RECORDER_LANE) != (rec == 1)) continue;
         if (rec == 0 && k->module && k->functions[0][k->acc] == nullptr) continue;
         for (int pf = 0; pf < 2; pf++) {
-            if (rec == 0 && pf == 1) continue; /* the uniform sweep has no prefetch */
             if (rec == 1 && c.sweep_prefetch != AD4CL_PREFETCH_AUTO && (c.sweep_prefetch == AD4CL_PREFETCH_ON) != (pf == 1)) continue;
             if (k->L.tape_in_smem && pf == 1) continue;
             for (int sh = 0; sh < k->nshapes; sh++) {
-                if (sh == 1 && (rec == 1 || !ls0)) continue; /* the one-group-per-SM shape pays with the uniform recorder in lock step only (measured) */
+                if (sh == 1 && (rec == 1 || !ls0 || pf == 1)) continue; /* the one-group-per-SM shape pays with the uniform recorder in lock step only (measured); it is for tapes that stay in L2, where a prefetch buys nothing */
                 cands.push_back({rec, pf, sh, ls0, 1e30f});
             }
         }

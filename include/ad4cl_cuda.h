@@ -77,8 +77,10 @@ enum {
                                an instance exists and was fully scalarised, else AD4CL_TAPE_HBM. */
 };
 
-/* L2 prefetch of tape rows two batches ahead in the sweep of the LANE recorder.  Helps a latency-bound
-   evaluation, costs a bandwidth-bound one a few percent; results are bit-identical either way. */
+/* L2 prefetch ahead of the sweep: the rows two batches below the ones being fetched (LANE recorder), the cells
+   three batches below (UNIFORM recorder; a cell's address does not depend on its header).  Helps a sweep that
+   waits on HBM latency (tape_stress 10^7 x 10^3: 35.8 -> 34.3 ms), costs one that is bound elsewhere a few
+   percent; results are bit-identical either way.  AUTO measures. */
 enum {
     AD4CL_PREFETCH_AUTO = -1,
     AD4CL_PREFETCH_OFF = 0,

@@ -129,7 +129,7 @@ def test_recorder_and_prefetch_choices_do_not_change_the_result(ctx, name, n, kw
     which an independent's contributions are summed over a warp differs); AUTO settles on one of them."""
     w = W.describe(name, n, **kw)
     out = {}
-    for rec, pf in (("lane", "off"), ("lane", "on"), ("uniform", "off"), ("auto", "auto")):
+    for rec, pf in (("lane", "off"), ("lane", "on"), ("uniform", "off"), ("uniform", "on"), ("auto", "auto")):
         k = W.bind(ctx, w, recorder=rec, prefetch=pf, tape="hbm")
         try:
             if rec == "auto":
@@ -146,6 +146,7 @@ def test_recorder_and_prefetch_choices_do_not_change_the_result(ctx, name, n, kw
             k.free()
     base = out[("lane", "off")]
     assert out[("lane", "on")][0] == base[0] and np.array_equal(out[("lane", "on")][1], base[1])
+    assert out[("uniform", "on")][0] == out[("uniform", "off")][0] and np.array_equal(out[("uniform", "on")][1], out[("uniform", "off")][1])
     for key in (("uniform", "off"), ("auto", "auto")):
         f, g = out[key]
         if w.nparams <= 16:
