@@ -213,11 +213,29 @@ __device__ __forceinline__ double apply_epilogue(double v, int c, int nparams, d
 __device__ __forceinline__ void finish_evaluation(const LaunchInfo& L, int ncols, int ngrad, double* scratch) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int nblocks = gridDim.x;
-    for (int c = warp; c < ncols; c += nw) {
-        double v = 0.0;
-        for (int b = lane; b < nblocks; b += 32) v += __ldcg(L.partials + (size_t) b * ncols + c);
-        v = warp_sum(v);
-        if (lane == 0) scratch[c] = v;
+    /* one CTA reads grid x ncols doubles: what it costs is load LATENCY, so every lane keeps 4 columns x 8 rows
+       of independent loads in flight (the additions stay in ascending block order per column) */
+    for (int c0 = warp; c0 < ncols; c0 += 4 * nw) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int b = lane; b < nblocks; b += 8 * 32) {
+            double t[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int bb = b + 32 * j, c = c0 + q * nw;
+                    t[q][j] = (bb < nblocks && c < ncols) ? __ldcg(L.partials + (size_t) bb * ncols + c) : 0.0;
+                }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[q] += t[q][j];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double s = warp_sum(v[q]);
+            if (lane == 0 && c0 + q * nw < ncols) scratch[c0 + q * nw] = s;
+        }
     }
     __syncthreads();
     bool ok = true;

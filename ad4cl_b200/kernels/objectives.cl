@@ -108,9 +108,13 @@ __kernel void regression_logistic(__global struct ad_gradient_structure* gs,
  *          [49,89) log F_year   89: a50   90: slope   91: log M
  *          92: log q   93: log sigma   [94,100) fleet deviations of log q
  *   d0   : observed log catch (this shard's observations)
- *   i1   : global index of this shard's first replicate (0 on one GPU): a multi-GPU
- *          run gives every rank a slice of the replicates of EVERY cell, so all
- *          shards have the same mix of tape lengths
+ *   i1   : how the shard maps its work-items to (cell, replicate):
+ *          i1 >= 0  replicate slices: the shard holds replicates [i1, i1 + i0) of EVERY cell
+ *                   (i0 = replicates per cell in the shard), so all shards have the same mix
+ *                   of tape lengths; one GPU: i1 = 0, i0 = R_global
+ *          i1 <  0  whole cells dealt round-robin: with p = -i1 - 1, the shard holds all
+ *                   i0 = R_global replicates of cells c0 + s*j, c0 = p % 1024, s = p / 1024
+ *                   (rank + world*j): long runs of identical work-items survive the sharding
  *   d1   : d1[0] = R_global, the replicates per cell of the WHOLE problem
  *   fleet of a replicate = rep*6/R_global  (6 contiguous blocks of replicates: the fleet
  *          deviation's parameter id is warp-uniform except at the 5 block boundaries)
@@ -138,8 +142,8 @@ __kernel void catch_at_age(__global struct ad_gradient_structure* gs,
     const int id = get_global_id(0);
     if (id < size) {
         const int R = i0;
-        const int rep = i1 + id % R;
-        const int cell = id / R;
+        const int rep = i1 >= 0 ? i1 + id % R : id % R;
+        const int cell = i1 >= 0 ? id / R : (-i1 - 1) % 1024 + ((-i1 - 1) / 1024) * (id / R);
         const int year = cell % CAA_YEARS;
         const int age = cell / CAA_YEARS;
         const int cohort = year - age + (CAA_AGES - 1);

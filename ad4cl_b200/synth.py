@@ -147,19 +147,21 @@ def caa_log_chat_table(theta: np.ndarray) -> np.ndarray:
     return tab
 
 
-def catch_at_age(n: int, rep0: int = 0, nrep: int | None = None):
-    """Observed log catch for the replicate slice [rep0, rep0 + nrep) of an n-observation problem
-    (n = 400 R): observation (cell, rep) with cell = year + 40 age has the global index
-    rep + R cell and sits at rep - rep0 + nrep * cell in the returned array (replicate fastest, so the
-    operator sequence is uniform across neighbouring work-items).  obs = ln Chat(theta*) + 0.3 N(0,1)
-    seed 4; evaluation point theta* + 0.02 N(0,1) seed 5.  Returns (obs, theta0, R)."""
+def catch_at_age(n: int, rep0: int = 0, nrep: int | None = None, cells=None):
+    """Observed log catch for the replicate slice [rep0, rep0 + nrep) of the cells `cells` (default: all 400)
+    of an n-observation problem (n = 400 R): observation (cell, rep) with cell = year + 40 age has the global
+    index rep + R cell and sits at rep - rep0 + nrep * j in the returned array, j the position of its cell in
+    `cells` (replicate fastest, so the operator sequence is uniform across neighbouring work-items).
+    obs = ln Chat(theta*) + 0.3 N(0,1) seed 4; evaluation point theta* + 0.02 N(0,1) seed 5.
+    Returns (obs, theta0, R)."""
     assert n % (CAA_YEARS * CAA_AGES) == 0, "catch-at-age needs n = 400 * replicates"
     R = n // (CAA_YEARS * CAA_AGES)
     nrep = R - rep0 if nrep is None else nrep
     th_true = caa_theta_true()
     tab = caa_log_chat_table(th_true)
-    cell = np.repeat(np.arange(CAA_YEARS * CAA_AGES, dtype=np.int64), nrep)
-    rep = rep0 + np.tile(np.arange(nrep, dtype=np.int64), CAA_YEARS * CAA_AGES)
+    cells = np.arange(CAA_YEARS * CAA_AGES, dtype=np.int64) if cells is None else np.asarray(cells, dtype=np.int64)
+    cell = np.repeat(cells, nrep)
+    rep = rep0 + np.tile(np.arange(nrep, dtype=np.int64), len(cells))
     year = cell % CAA_YEARS
     age = cell // CAA_YEARS
     fleet = (rep * CAA_FLEETS) // R      # 6 contiguous blocks of replicates

@@ -82,13 +82,27 @@ def describe(name: str, n: int, *, rank: int = 0, world: int = 1, steps: int = 3
                         max_ops=ops, max_slots=slots, ops_total=ops * count, slots_total=slots * count,
                         cells_total=cells * count, input_bytes=8 * (p + 1) * count)
     if name == "catch_at_age":
-        # tape length varies 4x with age: every rank takes a slice of the REPLICATES of every
-        # (year, age) cell, so all shards have the same mix (a contiguous observation range would not)
-        R = n // (synth.CAA_YEARS * synth.CAA_AGES)
+        # tape length varies 4x with age, so a contiguous observation range would give the ranks different
+        # mixes.  When the 400 (year, age) cells divide evenly, every rank takes WHOLE cells, dealt round-robin
+        # (cell = rank + world j: every age and a spread of years on every rank, and the long runs of identical
+        # work-items that the warp-uniform recorder and the lock-step work-groups live on stay as long as on one
+        # GPU); otherwise a slice of the REPLICATES of every cell (same mix on every rank, shorter runs).
+        ncell = synth.CAA_YEARS * synth.CAA_AGES
+        R = n // ncell
+        per_cell = _caa_per_cell()
+        if world > 1 and ncell % world == 0 and world < 1024:
+            mine = np.arange(rank, ncell, world)
+            obs, theta0, _ = synth.catch_at_age(n, 0, R, cells=mine)
+            ops = R * sum(per_cell[c][0] for c in mine)
+            slots = R * sum(per_cell[c][1] for c in mine)
+            cells = R * sum(per_cell[c][2] for c in mine)
+            return Workload(name, name, theta0, obs, np.array([float(R)]), len(obs), i0=R, i1=-(rank + 1024 * world) - 1,
+                            max_ops=128, max_slots=176, ops_total=ops, slots_total=slots, cells_total=cells,
+                            input_bytes=8 * len(obs))
         rep0, nrep = shard_range(R, rank, world)
         obs, theta0, _ = synth.catch_at_age(n, rep0, nrep)
         ops, slots = caa_totals(nrep)
-        cells = nrep * sum(c for _, _, c in _caa_per_cell())
+        cells = nrep * sum(c for _, _, c in per_cell)
         return Workload(name, name, theta0, obs, np.array([float(R)]), len(obs), i0=nrep, i1=rep0, max_ops=128, max_slots=176,
                         ops_total=ops, slots_total=slots, cells_total=cells, input_bytes=8 * len(obs))
     if name == "tape_stress":
