@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -377,26 +379,40 @@ int ad4cl_cuda_matrix_product_dense(ad4cl_context* ctx, int variant, int n, cons
     const int nblocks = (n / 64) * (n / 64);
     cudaError_t e = cudaSuccess;
     if (variant == 2) {
-        static unsigned* counters[64] = {};   /* per device, zero between launches (the kernel resets them) */
+        /* the two tile counters live with the CONTEXT (its launches are ordered by its stream; two contexts on
+           one device must not share them); zero between launches -- the kernel resets them */
+        static std::mutex mu;
+        static std::map<ad4cl_context*, unsigned*> counters_of;
+        static std::map<int, int> resident_of;
         int dev = 0;
         cudaGetDevice(&dev);
-        static int resident = 0;
-        if (!counters[dev & 63]) {
-            if (cudaMalloc(&counters[dev & 63], 2 * sizeof (unsigned)) != cudaSuccess
-                    || cudaMemset(counters[dev & 63], 0, 2 * sizeof (unsigned)) != cudaSuccess)
-                return ad4cl_cuda_set_error_(AD4CL_ERR_NOMEM, "dense path: counter allocation failed");
+        unsigned* counters = nullptr;
+        int resident = 0;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            unsigned*& slot = counters_of[ctx];
+            if (!slot) {
+                if (cudaMalloc(&slot, 2 * sizeof (unsigned)) != cudaSuccess || cudaMemset(slot, 0, 2 * sizeof (unsigned)) != cudaSuccess) {
+                    slot = nullptr;
+                    return ad4cl_cuda_set_error_(AD4CL_ERR_NOMEM, "dense path: counter allocation failed");
+                }
+            }
+            counters = slot;
+            int& res = resident_of[dev];
+            if (!res) {
+                int per_sm = 0, sms = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dgemm3_persistent, 128, 0);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                res = per_sm * sms;
+            }
+            resident = res;
         }
-        if (!resident) {
-            int per_sm = 0, sms = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dgemm3_persistent, 128, 0);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            resident = per_sm * sms;
-        }
+        if (resident < 1) return ad4cl_cuda_set_error_(AD4CL_ERR_CUDA, "dense path: the persistent kernel does not fit on this device");
         Gemm3 P;
         P.A = A_dev; P.B = B_dev; P.G = G_dev;
         P.C = (C_dev || sum_dev) ? (C_dev ? C_dev : scratch) : nullptr;
         P.dA = dA_dev; P.dB = dB_dev;
-        P.tile_sums = sums; P.sum_out = sum_dev; P.counters = counters[dev & 63]; P.n = n;
+        P.tile_sums = sums; P.sum_out = sum_dev; P.counters = counters; P.n = n;
         const int total = ((P.C ? 1 : 0) + (P.dA ? 1 : 0) + (P.dB ? 1 : 0)) * nblocks;
         if (total > 0) dgemm3_persistent<<<resident < total ? resident : total, 128, 0, st>>>(P);
         e = cudaGetLastError();

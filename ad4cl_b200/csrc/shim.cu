@@ -781,6 +781,8 @@ int autotune_recorder(ad4cl_kernel* k, const double* theta_dev) {
             }
         }
     }
+    if (cands.empty())   /* e.g. the uniform recorder was asked for a kernel with work-group barriers: keep what prepare() chose */
+        cands.push_back({k->recorder, k->L.sweep_prefetch, 0, ls0, 1e30f});
     auto apply = [&](const Cand& cd) {
         k->recorder = cd.recorder;
         if (k->module) k->function = k->functions[k->recorder][k->acc];
