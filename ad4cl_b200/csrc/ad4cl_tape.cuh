@@ -479,6 +479,12 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
         __match_all_sync(mask, word, &same);
         t->bad |= (!valid || !same || mask != 0xffffffffu) ? 1 : 0;
 #endif
+#if AD4CL_DEBUG_BOUNDS
+        if ((unsigned) (t->next_id - t->first_temp) >= (unsigned) (t->cap_id - t->first_temp - 1 + kGuardRows)) {
+            t->status |= kErrBounds;   /* the clamp of tape_close_op keeps the cursor inside the guard rows: never here */
+            return;
+        }
+#endif
         const int aux = UNIT == 0 ? (t->next_id - t->first_temp + kUnitCells) * kCellRowBytes
                                   : (UNIT > 0 ? 0 : kCellRowBytes);
         *reinterpret_cast<int2*> (t->hdr_b + (long long) t->next_id * kHdrBytes) = make_int2(word, aux);
@@ -497,6 +503,12 @@ __device__ __forceinline__ void tape_push(ThreadTape* t, double dx, int id, int 
             word = (int) (unsigned) r;
             t->status |= (int) (r >> 32);
         }
+#if AD4CL_DEBUG_BOUNDS
+        if ((unsigned) (t->next_id - t->first_temp) >= (unsigned) (t->cap_id - t->first_temp - 1 + kGuardRows)) {
+            t->status |= kErrBounds;
+            return;
+        }
+#endif
         *reinterpret_cast<double*> (t->rows_b + (long long) t->next_id * kRowBytes) = UNIT == 0 ? dx : (UNIT > 0 ? 1.0 : -1.0);
         *reinterpret_cast<int*> (t->ids_b + (long long) t->next_id * kRowBytes) = word;
         t->next_id++;
@@ -792,6 +804,27 @@ template <int MODE, bool PREFETCH>
 __device__ __forceinline__ void tape_sweep_uniform(ThreadTape& t, int out_id, double seed, const SweepTarget& T, PendingParam& pend) {
     int rows = sweep_seed<MODE>(t.next_id - t.first_temp, t.first_temp, t.wm1, out_id, seed, T);
     if (rows <= 0) return;
+#if AD4CL_DEBUG_BOUNDS
+    {   /* self-checking build: every header the sweep is about to follow is validated first, row r by lane
+           r mod 32 -- the cell offset names the +1 / -1 cell or the row's own cell, a temporary operand precedes
+           its use, an independent exists, far rows have a plane; anything else is reported, not swept */
+        const int cap_rows = t.cap_id - t.first_temp - 1 + kGuardRows;
+        int bad = rows > cap_rows ? 1 : 0;
+        for (int r = threadIdx.x & 31; r < rows && !bad; r += 32) {
+            const int2 h = *reinterpret_cast<const int2*> (tape_hdr(t) + (size_t) r * kHdrBytes);
+            const int word = h.x, cl = word & (kNopFlag | kParamFlag), pl = word & kIdMask;
+            const unsigned off = (unsigned) h.y;
+            if (!(off == 0u || off == (unsigned) kCellRowBytes || off == (unsigned) (kUnitCells + r) * kCellRowBytes)) bad = 1;
+            if (cl == 0 && pl >= r) bad = 1;
+            if (cl == kParamFlag && pl >= t.first_temp) bad = 1;
+            if ((word & (kFarFlag | kHasFarFlag)) && t.far_adj == nullptr) bad = 1;
+        }
+        if (__any_sync(0xffffffffu, bad)) {
+            t.status |= kErrBounds;
+            return;
+        }
+    }
+#endif
     /* pad to whole batches: the rows above `rows` are dead or were never written */
     const int nb = (rows + 3) >> 2;
 #pragma unroll

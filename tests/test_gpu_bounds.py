@@ -1,6 +1,8 @@
 """compute-sanitizer is not available on the GPU pool, so the library has a self-checking build
-(libad4cl_cuda_dbg.so, -DAD4CL_DEBUG_BOUNDS=1): every arena access of the tape machine is
-range-checked against the thread's own column and reported instead of executed.  This test runs
+(libad4cl_cuda_dbg.so, -DAD4CL_DEBUG_BOUNDS=1): the recorders check every push against the thread's own
+column, and both sweeps validate every id word / cell offset they are about to follow (operand precedes its
+use, independent exists, offset names the row's own cell or a unit cell, far rows have a plane); a violation is
+reported instead of executed.  This test runs
 examples/sanity_small.py (every device code path) against that build and requires identical output."""
 import os
 import subprocess
