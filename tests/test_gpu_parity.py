@@ -3,6 +3,8 @@ seeded inputs.  Tolerance: 1e-12 relative on the objective and on every gradient
 component (BASELINE.json north_star), the latter measured against the scale of
 the gradient, max(|g_ref|_inf, |g_ref_i|), because individual components may sit
 near a zero crossing (error metric)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -149,7 +151,9 @@ def test_recorder_and_prefetch_choices_do_not_change_the_result(ctx, name, n, kw
     assert out[("uniform", "on")][0] == out[("uniform", "off")][0] and np.array_equal(out[("uniform", "on")][1], out[("uniform", "off")][1])
     for key in (("uniform", "off"), ("auto", "auto")):
         f, g = out[key]
-        if w.nparams <= 16:
+        # bit equality between the two inlined copies of the objective holds for the release build (same FMA
+        # contraction in both); an A/B or self-checking build (AD4CL_CUDA_LIB) may contract them differently
+        if w.nparams <= 16 and "AD4CL_CUDA_LIB" not in os.environ:
             assert f == base[0] and np.array_equal(g, base[1])
         else:
             assert abs(f - base[0]) <= 1e-13 * abs(base[0])
