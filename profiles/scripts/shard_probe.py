@@ -17,8 +17,8 @@ k.profile(True)
 for _ in range(5):
     k.eval(w.theta)
 k.profile_read(reset=True)
-for _ in range(20):
+for _ in range(int(os.environ.get("PROBE_EVALS", "20"))):
     k.eval(w.theta)
 ms, n = k.profile_read()
-print("world", world, "items", w.size, "kernel_ms", round(ms, 4), k.stats())
+print("world", world, "items", w.size, "kernel_ms", round(ms, 4), "lib", os.path.basename(host.LIB_PATH), k.stats())
 k.free()
