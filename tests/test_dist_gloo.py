@@ -85,3 +85,37 @@ def test_epilogue_math():
     assert out[0].item() == 2.0 * (5.0 * (1.0 / 8.0)) and out[1].item() == -4.0 * (5.0 * (1.0 / 8.0))
     assert out[3].item() == 11.0 and out[4].item() == 12.0
     assert D.apply_epilogue(raw, 2, "sum", 10.0) is raw
+
+
+@pytest.mark.parametrize("name,n", [("catch_at_age", 8000), ("regression_linear", 1001), ("tape_stress", 333)])
+def test_shards_partition_the_problem_for_every_world_size(oracle_api, name, n):
+    """What `bench.py --gpus N` relies on at N = 1, 2, 4, 8 (and any other N): the shards workloads.describe hands
+    to the ranks partition the observations -- the raw sums S and dS/dtheta of the shards add up to the
+    single-shard values, and so do the operator / slot / input-byte totals the roofline is computed from.
+    catch-at-age switches layout with N: whole (year, age) cells dealt round-robin when N divides 400 (2, 4, 5, 8),
+    a slice of the replicates of every cell otherwise (3, 6, 7); both are the same kernel text, told apart by i1
+    (kernels/objectives.cl).  One process, the CPU oracle standing in for the device kernel."""
+    from ad4cl_b200 import workloads as W
+    orc = oracle_api.Port(False)
+
+    def raw(w):
+        r = orc.eval_objective(w.kernel, w.theta, w.d0, w.d1, w.size, w.i0, w.i1, epilogue=0, ops_per_item=w.max_ops)
+        return r["f"], np.asarray(r["grad"]), r["entries"] - w.size
+
+    whole = W.describe(name, n)
+    S, dS, ops = raw(whole)
+    assert ops == whole.ops_total
+    for world in range(2, 9):
+        shards = [W.describe(name, n, rank=r, world=world) for r in range(world)]
+        assert sum(w.size for w in shards) == whole.size
+        assert sum(w.ops_total for w in shards) == whole.ops_total
+        assert sum(w.slots_total for w in shards) == whole.slots_total
+        assert sum(w.input_bytes for w in shards) == whole.input_bytes
+        if name == "catch_at_age":   # the layout switch, as documented
+            assert all((w.i1 < 0) == (400 % world == 0) for w in shards)
+        parts = [raw(w) for w in shards]
+        assert [p[2] for p in parts] == [w.ops_total for w in shards]
+        Ssum = sum(p[0] for p in parts)
+        dSsum = np.sum([p[1] for p in parts], axis=0)
+        assert abs(Ssum - S) <= 1e-12 * abs(S), (world, Ssum, S)
+        assert np.max(np.abs(dSsum - dS)) <= 1e-12 * np.max(np.abs(dS)), world
